@@ -1,0 +1,218 @@
+/*
+ * seamless_b200.h - C ABI of the B200-native SeamlessM4T-v2 S2ST hot path.
+ *
+ * Convention: one `extern "C" int sb_<op>(...)` per module of the path, plain device pointers and
+ * sizes, a CUDA stream, an int return code (0 = ok, otherwise a negative SB_E* code; sb_last_error() gives text).
+ * Nothing here allocates device memory or synchronises; the caller owns every buffer.  This mirrors the reference's
+ * own native convention of one `extern "C" <Module>_forward(model, prefix, tensors...)` per module
+ * (ggml/examples/unity/fairseq2.h:153-250) loaded through ctypes (ggml/ggml.py:384-398).
+ *
+ * Activations are fp16, channels-last: a (B,T,C) tensor is a matrix of B*Tp rows by C columns where each sequence
+ * owns Tp = T + halos rows ("sequence layout": data row t of sequence b lives at row b*Tp + PH + t; halo rows are
+ * zero).  A dense tensor is the special case Tp = T, PH = 0.  Weights keep the reference's tensor layouts
+ * (nn.Linear (out,in); Conv1d repacked once by the host to (out, k, in)).
+ */
+#ifndef SEAMLESS_B200_H_
+#define SEAMLESS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* sb_stream_t; /* cudaStream_t */
+
+enum {
+  SB_OK = 0,
+  SB_EINVAL = -1,  /* bad argument */
+  SB_ECUDA = -2,   /* CUDA runtime / driver error */
+  SB_ENOSUP = -3   /* shape not supported by the kernels */
+};
+
+enum { SB_ACT_NONE = 0, SB_ACT_RELU = 1, SB_ACT_SILU = 2, SB_ACT_LRELU = 3, SB_ACT_TANH = 4 };
+
+const char* sb_last_error(void);
+int sb_version(void);
+/* number of kernels launched by this library since load (bench.py reports it as gpu_launches) */
+int64_t sb_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * sb_gemm - fused Linear / Conv1d-as-GEMM on tcgen05 tensor cores (TMA -> smem -> tcgen05.mma -> TMEM -> epilogue).
+ *   acc[m, n] = sum_{tap, c} A[a_row0 + m + tap*dil, c] * W[n, tap*c_in + c]
+ *   v   = act(acc + bias[n])            (glu: v[j] = (acc[2j]+b[2j]) * sigmoid(acc[2j+1]+b[2j+1]), N/2 outputs)
+ *   out[q, n] = gamma * (alpha * v + res1[q, n] + res2[q, n]),  q = m + out_row0
+ *   out2[q, n] = leaky_relu(out[q, n], out2_slope)                         (optional second output)
+ *   rows q whose sequence position is outside [0, len) are written as zeros (when seq_rows > 0).
+ * Replaces: fairseq2 Linear / torch Conv1d / ConvTranspose1d call sites of the path, e.g. Linear_forward
+ * (ggml/examples/unity/fairseq2.cpp:251), ggml_conv_1d in ConvModule_forward (fairseq2.cpp:698-731),
+ * Conv1dBlock.forward (models/unity/fft_decoder_layer.py:75-101), hifigan.py:114-121,180-196.
+ * ---------------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* a;       /* fp16 activations, row-major, row stride a_ld elements */
+  int64_t a_rows;      /* rows addressable from `a` (TMA bound; reads outside are zero) */
+  int64_t a_ld;        /* elements between rows (multiple of 8) */
+  int32_t c_in;        /* channels per tap */
+  int32_t taps;        /* 1 for Linear */
+  int32_t dil;         /* row step between taps */
+  int32_t a_row0;      /* window start of output row m=0 (may be negative) */
+  const void* w;       /* fp16 [n][taps*c_in] */
+  int32_t n;           /* output features before GLU */
+  int32_t m;           /* output rows */
+  const float* bias;   /* fp32 [n] or NULL */
+  int32_t act;         /* SB_ACT_* */
+  float act_slope;     /* leaky-relu slope */
+  int32_t glu;         /* 1: pairs (2j,2j+1) -> a*sigmoid(b) */
+  float alpha, gamma;
+  const void* res1; int64_t res1_ld;
+  const void* res2; int64_t res2_ld;
+  void* out; int64_t out_ld; int32_t out_f32;
+  void* out2; int64_t out2_ld; float out2_slope;
+  int64_t out_row0;
+  int32_t seq_rows;    /* Tp (0: no masking) */
+  int32_t seq_halo;    /* PH */
+  int32_t seq_len;     /* T when seq_lens == NULL */
+  const int32_t* seq_lens; /* per-sequence valid lengths or NULL */
+} sb_gemm_t;
+
+int sb_gemm(const sb_gemm_t* g, sb_stream_t stream);
+/* same contract on CUDA cores (fp32 accumulate); a debugging cross-check, never used by the product path */
+int sb_gemm_ref(const sb_gemm_t* g, sb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * sb_fbank - WaveformToFbankConverter(num_mel_bins=80, waveform_scale=2**15, standardize=...) on device.
+ * Replaces inference/translator.py:136-143,293 (fairseq2n knf path; arithmetic
+ * ggml/examples/kaldi-native-fbank/csrc/feature-window.cc:76-232, feature-fbank.cc:73-120).
+ *   wave  : fp32 [batch][wave_ld], num_samples[b] valid samples each
+ *   out   : fp16 [batch][out_frames_ld][80]; frames beyond the utterance are zero (Collater pad_value 0)
+ *   work  : fp32 [batch][out_frames_ld][80] scratch
+ *   frames_out : int32 [batch] number of frames per utterance (may be NULL)
+ * ---------------------------------------------------------------------------------------------------------------- */
+int sb_fbank(const float* wave, int64_t wave_ld, const int32_t* num_samples, int32_t batch, void* out,
+             int32_t out_frames_ld, float* work, int32_t* frames_out, int32_t standardize, sb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * sb_layernorm - y = LN(x (+ res)) * w + b over the last dim (eps 1e-5), fp16 io, fp32 statistics.
+ * Rows are addressed in sequence layout on both sides; rows at positions >= len are written as zeros when
+ * mask_out != 0.  Replaces LayerNorm_forward (fairseq2.cpp:266).
+ * ---------------------------------------------------------------------------------------------------------------- */
+int sb_layernorm(const void* x, const void* res, void* y, void* sum_out, const float* w, const float* b, int32_t dim,
+                 int32_t batch, int32_t T, int32_t in_rows, int32_t in_halo, int32_t out_rows, int32_t out_halo,
+                 const int32_t* lens, int32_t mask_out, sb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * sb_attention - multi-head scaled dot-product attention, head_dim 64, fp16 io, fp32 softmax, flash-style.
+ *   scores = (q.k^T + q.rel_k[clamp(j-i,-left,right)+left]) / 8, key mask j < kv_lens[b], optional causal mask.
+ * q/k/v/out pointers address row 0 of sequence 0 (sequence layout given by *_rows/*_halo), *_ld = row stride.
+ * Replaces MultiheadAttention_forward (fairseq2.cpp:399-499) and ShawRelativePositionSDPA
+ * (models/conformer_shaw/builder.py:127-146).
+ * ---------------------------------------------------------------------------------------------------------------- */
+int sb_attention(const void* q, int64_t q_ld, const void* k, int64_t k_ld, const void* v, int64_t v_ld, void* out,
+                 int64_t out_ld, int32_t batch, int32_t heads, int32_t sq, int32_t sk, int32_t q_rows, int32_t q_halo,
+                 int32_t kv_rows, int32_t kv_halo, const int32_t* kv_lens, int32_t causal, const void* rel_k,
+                 int32_t rel_left, int32_t rel_right, sb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * sb_dwconv_ln_silu - Conformer conv module middle: causal depthwise Conv1d(k) -> LayerNorm(C) -> SiLU.
+ * Replaces ConformerConvolution's depthwise_conv/layer_norm/activation (conformer_shaw/builder.py:148-156;
+ * op order fairseq2.cpp:698-731 with the v2 causal + LayerNorm variant).  x,y dense (B,T,C) fp16; w [C][k] fp16.
+ * ---------------------------------------------------------------------------------------------------------------- */
+int sb_dwconv_ln_silu(const void* x, void* y, const void* w, const float* ln_w, const float* ln_b, int32_t batch,
+                      int32_t T, int32_t C, int32_t k, sb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Text decoder step pieces (KV cache with beam-ancestor indirection instead of the reference's per-step
+ * index_select copies, fairseq2.cpp:170-198).
+ * ---------------------------------------------------------------------------------------------------------------- */
+/* The step index of the incremental decoder lives in device memory (*step_ptr) so that ONE captured CUDA graph of a
+ * decoder step can be replayed for every position; sb_step_advance increments it at the end of the graph.
+ * x[r] = embed[tok[r]] * scale + pos[step]; tok = seqs[r*seq_ld + step]  (fairseq2.cpp:917-953); pos_table fp32. */
+int sb_embed_step(const int32_t* seqs, int32_t seq_ld, const int32_t* step_ptr, const void* embed, const void* pos_table,
+                  float scale, void* x, int32_t rows, int32_t dim, sb_stream_t stream);
+int sb_step_advance(int32_t* step_ptr, sb_stream_t stream);
+/* embeds a full (rows, L) id matrix (teacher-forced pass): x[(r*L+t)] = embed[ids[r*ids_ld+t]]*scale + pos[t] */
+int sb_embed_seq(const int32_t* ids, int32_t ids_ld, int32_t L, const void* embed, const void* pos_table, float scale,
+                 void* x, int32_t rows, int32_t dim, sb_stream_t stream);
+/* self-attention of one new token per row against the cache.
+ *   qkv: fp16 [rows][3*dim] (q|k|v of the new token); kcache/vcache: fp16 [max_len][rows][dim];
+ *   anc: int32 [rows][anc_ld], anc[r][t] = cache slot holding position t of row r's history (t < step);
+ *   the new k/v are stored to slot r at position `step`.  out: fp16 [rows][dim]. */
+int sb_decode_self_attn(const void* qkv, void* kcache, void* vcache, const int32_t* anc, int32_t anc_ld,
+                        const int32_t* step_ptr, int32_t max_len, void* out, int32_t rows, int32_t heads,
+                        sb_stream_t stream);
+/* cross-attention of one token per row against per-utterance static K/V: k/v fp16 [batch][s_enc][dim] (row stride
+ * kv_ld), row r attends utterance r / beam. */
+int sb_decode_cross_attn(const void* q, const void* k, const void* v, int64_t kv_ld, const int32_t* enc_lens,
+                         int32_t s_enc, void* out, int32_t rows, int32_t beam, int32_t heads, sb_stream_t stream);
+/* per row: log-softmax statistics and the top-K candidates of an fp32 logit row.
+ *   cand_val [rows][K] = lprob, cand_idx [rows][K]; eos_lprob[rows] = lprob of eos; pad is never a candidate. */
+int sb_logits_topk(const float* logits, int64_t ld, int32_t rows, int32_t vocab, int32_t pad_idx, int32_t eos_idx,
+                   int32_t unk_idx, float unk_penalty, int32_t K, float* cand_val, int32_t* cand_idx, float* eos_lprob,
+                   sb_stream_t stream);
+
+/* one beam-search step for every sentence (BeamSearchSeq2SeqGenerator step, mirrored fairseq2.cpp:1463-1594).
+ * State (all device, int32/fp32):
+ *   seqs [B*beam][max_len], scores [B*beam][max_len], anc [B*beam][max_len],
+ *   fin_count [B], fin_score [B][beam], fin_len [B][beam], fin_seqs [B][beam][max_len], active [B] */
+typedef struct {
+  int32_t batch, beam, max_len, vocab, K;
+  const int32_t* step_ptr; /* position being consumed; the new token goes to step+1 */
+  int32_t prefix_len;      /* at step == prefix_len-1 only beam 0 of each sentence is a candidate source */
+  int32_t eos_idx;
+  int32_t min_len;     /* EOS forbidden while step < min_len */
+  float len_penalty;
+  const float* cand_val; const int32_t* cand_idx; const float* eos_lprob;
+  int32_t* seqs; float* scores; int32_t* anc;  /* reordered in place */
+  int32_t* fin_count; float* fin_score; int32_t* fin_len; int32_t* fin_seqs; int32_t* active;
+  int32_t* n_active;   /* [1] number of sentences still searching (written every step) */
+} sb_beam_t;
+int sb_beam_step(const sb_beam_t* p, sb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * NAR T2U frontend (models/unity/nar_decoder_frontend.py:130-334, length_regulator.py:24-39,275-321) on device.
+ * ---------------------------------------------------------------------------------------------------------------- */
+/* text ids -> per-subword char lengths + char id sequence, using per-token tables built once from the vocab:
+ *   tok_len[v] (chars in piece), tok_flags[v] (bit0 punct, bit1 starts-with-space-and-longer-than-1),
+ *   tok_chars[v][max_chars] char ids.  text_seqs [B][L] (already [:, :-1]-trimmed, generator.py:287).
+ *   char_lens [B][L] (incl. the two zero pads of TagManager), char_seqs [B][max_c] (filled with text pad),
+ *   char_seq_lens [B]. */
+int sb_text_to_chars(const int32_t* text_seqs, int32_t L, int32_t batch, const uint8_t* tok_len,
+                     const uint8_t* tok_flags, const int32_t* tok_chars, int32_t max_chars, int32_t pad_idx,
+                     int32_t unk_idx, int32_t eos_idx, int32_t* char_lens, int32_t* char_seqs, int32_t max_c,
+                     int32_t* char_seq_lens, sb_stream_t stream);
+/* HardUpsampling + additive terms: y[b][u] = x[b][src(u)] + alpha*pos[u] + (emb ? emb[ids[b][u]]*emb_scale : 0)
+ * for u < sum(dur[b]); zeros beyond... (+ pos/emb exactly as the reference adds them to padded rows too).
+ *   x in sequence layout (x_rows,x_halo), y in sequence layout (y_rows,y_halo), U = y logical length. */
+int sb_upsample_add(const void* x, int32_t x_rows, int32_t x_halo, int32_t S, const int32_t* dur, void* y,
+                    int32_t y_rows, int32_t y_halo, int32_t U, int32_t batch, int32_t dim, const void* pos_table,
+                    const float* alpha, const void* emb, const int32_t* ids, int32_t ids_ld, float emb_scale,
+                    int32_t* out_lens, sb_stream_t stream);
+/* durations = clamp(round((exp(logd)-1)*factor), min 1) * mask  (length_regulator.py:286-293) */
+int sb_durations(const void* hidden, int32_t rows_ld, int32_t halo, const void* proj_w, float proj_b, int32_t dim,
+                 const int32_t* lens, int32_t batch, int32_t S, float factor, int32_t* dur, sb_stream_t stream);
+/* unit logits argmax with the tied projection done by sb_gemm into fp32: units = decode(argmax) (generator.py:346-353,
+ * unit_tokenizer.py:231-241): pad beyond lens, eos->pad, pad->pad+4, -4.  units int32 [B][U] */
+int sb_unit_argmax(const float* logits, int64_t ld, int32_t rows_per_seq, int32_t halo, int32_t U, int32_t batch,
+                   int32_t vocab, const int32_t* lens, int32_t pad_idx, int32_t eos_idx, int32_t* units,
+                   sb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Vocoder glue (models/vocoder/codehifigan.py:75-101): x[b][u] = [lang | dict[unit] | spkr] into a sequence-layout
+ * buffer; everything else of the HiFi-GAN generator is sb_gemm with fused epilogues.
+ * ---------------------------------------------------------------------------------------------------------------- */
+int sb_vocoder_embed(const int32_t* units, int32_t U, int32_t batch, const void* dict, int32_t dict_dim,
+                     const void* lang, int32_t lang_dim, const int32_t* lang_idx, const void* spkr, int32_t spkr_dim,
+                     const int32_t* spkr_idx, void* x, int32_t x_rows, int32_t x_halo, sb_stream_t stream);
+/* final conv_post (C->1, k7) + tanh on CUDA cores: wav fp32 [B][T] from lrelu'ed activations in sequence layout */
+int sb_conv_post_tanh(const void* x, int32_t x_rows, int32_t x_halo, int32_t T, int32_t C, int32_t batch,
+                      const void* w, float bias, int32_t k, float* wav, int64_t wav_ld, sb_stream_t stream);
+
+/* small utilities */
+int sb_cast_f32_to_f16(const float* src, void* dst, int64_t n, sb_stream_t stream);
+int sb_fill_zero(void* dst, int64_t bytes, sb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEAMLESS_B200_H_ */

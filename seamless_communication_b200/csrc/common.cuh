@@ -1,0 +1,77 @@
+// Shared device/host helpers for the sm_100a kernels.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/seamless_b200.h"
+
+namespace sb {
+
+typedef __half elem_t;  // storage / tensor-core input type of the whole path (the reference runs fp16 on CUDA,
+                        // cli/m4t/predict/predict.py:207-212)
+
+void set_error(const char* fmt, ...);
+extern long long g_launch_count;
+inline void count_launch(int n = 1) { g_launch_count += n; }
+
+#define SB_REQUIRE(cond, code, ...)      \
+  do {                                   \
+    if (!(cond)) {                       \
+      sb::set_error(__VA_ARGS__);        \
+      return (code);                     \
+    }                                    \
+  } while (0)
+
+#define SB_CUDA_OK(expr)                                                                 \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess) {                                                             \
+      sb::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return SB_ECUDA;                                                                   \
+    }                                                                                    \
+  } while (0)
+
+#define SB_LAUNCH_OK()                                                                   \
+  do {                                                                                   \
+    cudaError_t _e = cudaGetLastError();                                                 \
+    if (_e != cudaSuccess) {                                                             \
+      sb::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return SB_ECUDA;                                                                   \
+    }                                                                                    \
+    sb::count_launch();                                                                  \
+  } while (0)
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+__device__ __forceinline__ float apply_act(float v, int act, float slope) {
+  switch (act) {
+    case SB_ACT_RELU: return fmaxf(v, 0.f);
+    case SB_ACT_SILU: return v / (1.f + __expf(-v));
+    case SB_ACT_LRELU: return v > 0.f ? v : v * slope;
+    case SB_ACT_TANH: return tanhf(v);
+    default: return v;
+  }
+}
+
+// sequence layout helper: is padded-row q a valid data row?  (q = b*Tp + PH + t, 0 <= t < len[b])
+__device__ __forceinline__ bool seq_row_valid(long long q, int Tp, int PH, int T, const int* lens) {
+  if (Tp <= 0) return true;
+  int b = (int)(q / Tp);
+  int pos = (int)(q - (long long)b * Tp) - PH;
+  int len = lens ? lens[b] : T;
+  return pos >= 0 && pos < len;
+}
+
+}  // namespace sb

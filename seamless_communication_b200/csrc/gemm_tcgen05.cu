@@ -1,0 +1,480 @@
+// sb_gemm: fused Linear / Conv1d-as-GEMM for sm_100a.
+//
+//   TMA (cp.async.bulk.tensor, 128B swizzle) -> 3/4-stage smem ring -> tcgen05.mma (kind::f16, fp32 accumulate in
+//   TMEM, issued by one thread) -> tcgen05.ld epilogue (bias, activation / GLU, residuals, sequence mask, fp16|fp32
+//   store, optional leaky-relu'd second output).
+//
+// Warp roles (192 threads): warps 0-3 epilogue (TMEM lane quarter = warp id), warp 4 TMA producer, warp 5 MMA issuer
+// + TMEM allocator.  One 128 x BN output tile per CTA; 2 CTAs co-reside per SM (<= 96 KB smem, <= 128 TMEM columns
+// each) so one CTA's epilogue overlaps the other's main loop.
+//
+// Conv taps are realised purely through the TMA row coordinate: tap j of output row m reads A row
+// a_row0 + m + j*dil, the weight K index is j*c_in + c.  Rows outside [0, a_rows) and channels >= c_in are
+// zero-filled by TMA, so c_in need not be a multiple of 64.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace sb {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 fp16 = 128 B = one swizzle atom row
+constexpr int A_TILE_BYTES = BM * BK * 2;
+
+struct GemmArgs {
+  int m, n, c_in, taps, dil, a_row0;
+  const float* bias;
+  int act;
+  float act_slope;
+  int glu;
+  float alpha, gamma;
+  const elem_t* res1;
+  long long res1_ld;
+  const elem_t* res2;
+  long long res2_ld;
+  void* out;
+  long long out_ld;
+  int out_f32;
+  elem_t* out2;
+  long long out2_ld;
+  float out2_slope;
+  long long out_row0;
+  int seq_rows, seq_halo, seq_len;
+  const int* seq_lens;
+};
+
+// ---------------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait: a protocol bug traps (visible as a CUDA error) instead of hanging the GPU box
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 24)) {
+      printf("sb_gemm: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, both operands K-major
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major, 128B-swizzled operand tile: rows of 128 B, 8-row atoms 1024 B apart (SBO), LBO unused.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);  // start address  [0,14)
+  d |= (uint64_t)(1024 >> 4) << 32;             // stride byte offset [32,46)
+  d |= (uint64_t)1 << 46;                       // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                       // layout: SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+template <int BN>
+struct TileCfg {
+  static constexpr int STAGES = (BN >= 128) ? 3 : 4;
+  static constexpr int B_TILE_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+  static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + BN * 4;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(192, (BN >= 128) ? 2 : 2)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmArgs g) {
+  using Cfg = TileCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = (uint64_t*)(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_ptr_smem = (uint32_t*)(tmem_full_bar + 1);
+  float* bias_s = (float*)(smem + STAGES * Cfg::STAGE_BYTES + 256);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN;
+  const int m0 = blockIdx.y * BM;
+  const int cblocks = (g.c_in + BK - 1) / BK;
+  const int kblocks = g.taps * cblocks;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 5) {  // TMEM allocation (whole warp), address lands in smem
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
+                 "r"((uint32_t)Cfg::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp < 4) {
+    for (int i = threadIdx.x; i < BN; i += 128) {
+      int n = n0 + i;
+      bias_s[i] = (g.bias != nullptr && n < g.n) ? g.bias[n] : 0.f;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 4) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      for (int kb = 0; kb < kblocks; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+        const int tap = kb / cblocks, c0 = (kb - tap * cblocks) * BK;
+        uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
+        tma_load_2d(sa, &tmA, &full_bar[s], c0, m0 + g.a_row0 + tap * g.dil);
+        tma_load_2d(sa + A_TILE_BYTES, &tmW, &full_bar[s], tap * g.c_in + c0, n0);
+      }
+    }
+  } else if (warp == 5) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A=B=f16 (0) / bf16 (1), K-major both, N>>3, M>>4
+      const uint32_t idesc = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      for (int kb = 0; kb < kblocks; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES);
+        const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + A_TILE_BYTES);
+        const int tap = kb / cblocks, c0 = (kb - tap * cblocks) * BK;
+        int ksteps = (g.c_in - c0 + 15) / 16;
+        if (ksteps > BK / 16) ksteps = BK / 16;
+        for (int k = 0; k < ksteps; ++k) {
+          // advance 16 elements (32 B) along K inside the swizzle atom: +2 in the (addr >> 4) field
+          tc_mma_f16(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+        }
+        tc_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
+      }
+      tc_commit(tmem_full_bar);    // accumulator complete
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 0..3)
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const int row = warp * 32 + lane;
+    const long long m = (long long)m0 + row;
+    const bool row_ok = m < g.m;
+    const long long q = m + g.out_row0;
+    const bool valid = row_ok && seq_row_valid(q, g.seq_rows, g.seq_halo, g.seq_len, g.seq_lens);
+    const int n_out_total = g.glu ? g.n / 2 : g.n;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      if (n0 + c0 >= g.n) break;  // warp-uniform
+      uint32_t r[32];
+      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
+      if (!row_ok) continue;
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + bias_s[c0 + j];
+      int nv = 32;         // number of output values in this chunk
+      int oc = n0 + c0;    // first output column
+      if (g.glu) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = v[2 * j] / (1.f + __expf(-v[2 * j + 1]));
+        nv = 16;
+        oc = (n0 + c0) >> 1;
+      } else if (g.act != SB_ACT_NONE) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], g.act, g.act_slope);
+      }
+      const bool full = (oc + nv <= n_out_total);
+      // residuals
+      if (valid && (g.res1 != nullptr || g.res2 != nullptr)) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] *= g.alpha;
+        const elem_t* rp[2] = {g.res1, g.res2};
+        const long long rl[2] = {g.res1_ld, g.res2_ld};
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          if (rp[t] == nullptr) continue;
+          const elem_t* p = rp[t] + q * rl[t] + oc;
+          if (full && ((rl[t] | oc) & 7) == 0) {
+            for (int j = 0; j < nv; j += 8) {
+              uint4 u = *reinterpret_cast<const uint4*>(p + j);
+              const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float2 f = __half22float2(h[e]);
+                v[j + 2 * e] += f.x;
+                v[j + 2 * e + 1] += f.y;
+              }
+            }
+          } else {
+            for (int j = 0; j < nv; ++j)
+              if (oc + j < n_out_total) v[j] += __half2float(p[j]);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] *= g.gamma;
+      } else {
+        const float sc = g.alpha * g.gamma;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] *= sc;
+      }
+      if (!valid) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+      }
+      // stores
+      if (g.out_f32) {
+        float* p = reinterpret_cast<float*>(g.out) + q * g.out_ld + oc;
+        if (full && ((g.out_ld | oc) & 3) == 0) {
+          for (int j = 0; j < nv; j += 4) *reinterpret_cast<float4*>(p + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+          for (int j = 0; j < nv; ++j)
+            if (oc + j < n_out_total) p[j] = v[j];
+        }
+      } else {
+        elem_t* p = reinterpret_cast<elem_t*>(g.out) + q * g.out_ld + oc;
+        if (full && ((g.out_ld | oc) & 7) == 0) {
+          for (int j = 0; j < nv; j += 8) {
+            uint4 u;
+            __half2* h = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(v[j + 2 * e], v[j + 2 * e + 1]);
+            *reinterpret_cast<uint4*>(p + j) = u;
+          }
+        } else {
+          for (int j = 0; j < nv; ++j)
+            if (oc + j < n_out_total) p[j] = __float2half_rn(v[j]);
+        }
+      }
+      if (g.out2 != nullptr) {
+        elem_t* p = g.out2 + q * g.out2_ld + oc;
+        if (full && ((g.out2_ld | oc) & 7) == 0) {
+          for (int j = 0; j < nv; j += 8) {
+            uint4 u;
+            __half2* h = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float a = v[j + 2 * e], b = v[j + 2 * e + 1];
+              h[e] = __floats2half2_rn(a > 0.f ? a : a * g.out2_slope, b > 0.f ? b : b * g.out2_slope);
+            }
+            *reinterpret_cast<uint4*>(p + j) = u;
+          }
+        } else {
+          for (int j = 0; j < nv; ++j)
+            if (oc + j < n_out_total) p[j] = __float2half_rn(v[j] > 0.f ? v[j] : v[j] * g.out2_slope);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 2D fp16 tensor (inner = channels, outer = rows), box 64 x box_rows, 128B swizzle, OOB -> 0
+static int make_tmap(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t rows, uint64_t ld_elems,
+                     uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  SB_REQUIRE(fn != nullptr, SB_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {inner, rows};
+  cuuint64_t strides[1] = {ld_elems * 2};
+  cuuint32_t box[2] = {BK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SB_REQUIRE(r == CUDA_SUCCESS, SB_ECUDA, "cuTensorMapEncodeTiled failed (%d): inner=%llu rows=%llu ld=%llu", (int)r,
+             (unsigned long long)inner, (unsigned long long)rows, (unsigned long long)ld_elems);
+  return SB_OK;
+}
+
+static int validate(const sb_gemm_t* g) {
+  SB_REQUIRE(g != nullptr && g->a != nullptr && g->w != nullptr && g->out != nullptr, SB_EINVAL, "sb_gemm: null operand");
+  SB_REQUIRE(g->m > 0 && g->n > 0 && g->c_in > 0 && g->taps > 0, SB_EINVAL, "sb_gemm: bad shape m=%d n=%d c_in=%d taps=%d",
+             g->m, g->n, g->c_in, g->taps);
+  SB_REQUIRE((g->a_ld % 8) == 0 && (g->c_in % 8) == 0, SB_ENOSUP, "sb_gemm: a_ld (%lld) and c_in (%d) must be multiples of 8",
+             (long long)g->a_ld, g->c_in);
+  SB_REQUIRE(((uintptr_t)g->a % 16) == 0 && ((uintptr_t)g->w % 16) == 0, SB_EINVAL, "sb_gemm: operands must be 16B aligned");
+  SB_REQUIRE(!g->glu || (g->n % 2) == 0, SB_EINVAL, "sb_gemm: glu needs even n");
+  return SB_OK;
+}
+
+static void fill_args(const sb_gemm_t* g, GemmArgs* a) {
+  a->m = g->m; a->n = g->n; a->c_in = g->c_in; a->taps = g->taps; a->dil = g->dil; a->a_row0 = g->a_row0;
+  a->bias = g->bias; a->act = g->act; a->act_slope = g->act_slope; a->glu = g->glu;
+  a->alpha = g->alpha; a->gamma = g->gamma;
+  a->res1 = (const elem_t*)g->res1; a->res1_ld = g->res1_ld; a->res2 = (const elem_t*)g->res2; a->res2_ld = g->res2_ld;
+  a->out = g->out; a->out_ld = g->out_ld; a->out_f32 = g->out_f32;
+  a->out2 = (elem_t*)g->out2; a->out2_ld = g->out2_ld; a->out2_slope = g->out2_slope;
+  a->out_row0 = g->out_row0;
+  a->seq_rows = g->seq_rows; a->seq_halo = g->seq_halo; a->seq_len = g->seq_len; a->seq_lens = g->seq_lens;
+}
+
+template <int BN>
+static int launch(const sb_gemm_t* g, cudaStream_t st) {
+  using Cfg = TileCfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    SB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  CUtensorMap tmA, tmW;
+  int rc = make_tmap(&tmA, g->a, (uint64_t)g->c_in, (uint64_t)g->a_rows, (uint64_t)g->a_ld, BM);
+  if (rc) return rc;
+  rc = make_tmap(&tmW, g->w, (uint64_t)g->taps * g->c_in, (uint64_t)g->n, (uint64_t)g->taps * g->c_in, BN);
+  if (rc) return rc;
+  GemmArgs args;
+  fill_args(g, &args);
+  dim3 grid((g->n + BN - 1) / BN, (g->m + BM - 1) / BM);
+  gemm_tc_kernel<BN><<<grid, 192, Cfg::SMEM_BYTES, st>>>(tmA, tmW, args);
+  SB_LAUNCH_OK();
+  return SB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- CUDA-core cross-check
+__global__ void gemm_ref_kernel(const elem_t* __restrict__ A, long long a_rows, long long a_ld, const elem_t* __restrict__ W,
+                                const GemmArgs g) {
+  const int n_out_total = g.glu ? g.n / 2 : g.n;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)g.m * n_out_total) return;
+  const long long m = idx / n_out_total;
+  const int oc = (int)(idx - m * n_out_total);
+  const long long ktot = (long long)g.taps * g.c_in;
+  auto dot = [&](int n) {
+    float acc = 0.f;
+    for (int t = 0; t < g.taps; ++t) {
+      long long r = m + g.a_row0 + (long long)t * g.dil;
+      if (r < 0 || r >= a_rows) continue;
+      const elem_t* ap = A + r * a_ld;
+      const elem_t* wp = W + (long long)n * ktot + (long long)t * g.c_in;
+      for (int c = 0; c < g.c_in; ++c) acc += __half2float(ap[c]) * __half2float(wp[c]);
+    }
+    return acc + (g.bias ? g.bias[n] : 0.f);
+  };
+  float v;
+  if (g.glu) {
+    float a = dot(2 * oc), b = dot(2 * oc + 1);
+    v = a / (1.f + __expf(-b));
+  } else {
+    v = apply_act(dot(oc), g.act, g.act_slope);
+  }
+  const long long q = m + g.out_row0;
+  const bool valid = seq_row_valid(q, g.seq_rows, g.seq_halo, g.seq_len, g.seq_lens);
+  if (g.res1 != nullptr || g.res2 != nullptr) {
+    v *= g.alpha;
+    if (g.res1) v += __half2float(g.res1[q * g.res1_ld + oc]);
+    if (g.res2) v += __half2float(g.res2[q * g.res2_ld + oc]);
+    v *= g.gamma;
+  } else {
+    v *= g.alpha * g.gamma;
+  }
+  if (!valid) v = 0.f;
+  if (g.out_f32) reinterpret_cast<float*>(g.out)[q * g.out_ld + oc] = v;
+  else reinterpret_cast<elem_t*>(g.out)[q * g.out_ld + oc] = __float2half_rn(v);
+  if (g.out2) g.out2[q * g.out2_ld + oc] = __float2half_rn(v > 0.f ? v : v * g.out2_slope);
+}
+
+}  // namespace sb
+
+extern "C" int sb_gemm(const sb_gemm_t* g, sb_stream_t stream) {
+  int rc = sb::validate(g);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long mt = (g->m + sb::BM - 1) / sb::BM;
+  auto tiles = [&](int bn) { return mt * ((g->n + bn - 1) / bn); };
+  // largest N tile that still gives every SM two CTAs; fall back to smaller tiles for skinny problems
+  if (g->n >= 128 && tiles(128) >= 148) return sb::launch<128>(g, st);
+  if (g->n >= 64 && tiles(64) >= 148) return sb::launch<64>(g, st);
+  if (g->n > 64) return sb::launch<64>(g, st);
+  return sb::launch<32>(g, st);
+}
+
+extern "C" int sb_gemm_ref(const sb_gemm_t* g, sb_stream_t stream) {
+  int rc = sb::validate(g);
+  if (rc) return rc;
+  sb::GemmArgs args;
+  sb::fill_args(g, &args);
+  const int n_out = g->glu ? g->n / 2 : g->n;
+  long long total = (long long)g->m * n_out;
+  int threads = 256;
+  long long blocks = (total + threads - 1) / threads;
+  sb::gemm_ref_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>((const sb::elem_t*)g->a, g->a_rows, g->a_ld,
+                                                                            (const sb::elem_t*)g->w, args);
+  SB_LAUNCH_OK();
+  return SB_OK;
+}

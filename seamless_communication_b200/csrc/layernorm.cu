@@ -1,0 +1,114 @@
+// sb_layernorm: row LayerNorm (eps 1e-5) with optional residual add, sequence-layout remap and padding mask.
+// One warp per row, 16-byte loads, fp32 statistics (two-pass over registers).  HBM-bound: 2*dim*2 B per row.
+#include "common.cuh"
+
+namespace sb {
+
+constexpr int LN_MAX_CHUNKS = 8;  // dim <= 8 * 256 = 2048
+
+__global__ void __launch_bounds__(256) layernorm_kernel(const elem_t* __restrict__ x, const elem_t* __restrict__ res,
+                                                        elem_t* __restrict__ y, elem_t* __restrict__ sum_out,
+                                                        const float* __restrict__ w, const float* __restrict__ bvec, int dim,
+                                                        long long total_rows, int T, int in_rows, int in_halo, int out_rows,
+                                                        int out_halo, const int* __restrict__ lens, int mask_out) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= total_rows) return;
+  const int b = (int)(row / T), t = (int)(row - (long long)b * T);
+  const long long rin = (long long)b * in_rows + in_halo + t, rout = (long long)b * out_rows + out_halo + t;
+  const elem_t* xp = x + rin * dim;
+  elem_t* yp = y + rout * dim;
+  const bool masked = mask_out && lens != nullptr && t >= lens[b];
+  const int nchunk = (dim + 255) / 256;
+  float v[LN_MAX_CHUNKS][8];
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < LN_MAX_CHUNKS; ++c) {
+    if (c >= nchunk) break;
+    const int off = c * 256 + lane * 8;
+    if (off < dim) {
+      uint4 u = *reinterpret_cast<const uint4*>(xp + off);
+      const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float2 f = __half22float2(h[e]);
+        v[c][2 * e] = f.x;
+        v[c][2 * e + 1] = f.y;
+      }
+      if (res != nullptr) {
+        uint4 u2 = *reinterpret_cast<const uint4*>(res + rin * dim + off);
+        const __half2* h2 = reinterpret_cast<const __half2*>(&u2);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float2 f = __half22float2(h2[e]);
+          v[c][2 * e] += f.x;
+          v[c][2 * e + 1] += f.y;
+        }
+        if (sum_out != nullptr) {
+          uint4 o;
+          __half2* ho = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) ho[e] = __floats2half2_rn(v[c][2 * e], v[c][2 * e + 1]);
+          *reinterpret_cast<uint4*>(sum_out + rout * dim + off) = o;
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s += v[c][e];
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[c][e] = 0.f;
+    }
+  }
+  const float mean = warp_sum(s) / dim;
+  float sq = 0.f;
+#pragma unroll
+  for (int c = 0; c < LN_MAX_CHUNKS; ++c) {
+    if (c >= nchunk) break;
+    const int off = c * 256 + lane * 8;
+    if (off < dim) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float d = v[c][e] - mean;
+        sq += d * d;
+      }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / dim + 1e-5f);
+#pragma unroll
+  for (int c = 0; c < LN_MAX_CHUNKS; ++c) {
+    if (c >= nchunk) break;
+    const int off = c * 256 + lane * 8;
+    if (off < dim) {
+      float4 w0 = *reinterpret_cast<const float4*>(w + off), w1 = *reinterpret_cast<const float4*>(w + off + 4);
+      float4 b0 = *reinterpret_cast<const float4*>(bvec + off), b1 = *reinterpret_cast<const float4*>(bvec + off + 4);
+      const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      uint4 o;
+      __half2* ho = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float a0 = masked ? 0.f : (v[c][2 * e] - mean) * rstd * ww[2 * e] + bb[2 * e];
+        float a1 = masked ? 0.f : (v[c][2 * e + 1] - mean) * rstd * ww[2 * e + 1] + bb[2 * e + 1];
+        ho[e] = __floats2half2_rn(a0, a1);
+      }
+      *reinterpret_cast<uint4*>(yp + off) = o;
+    }
+  }
+}
+
+}  // namespace sb
+
+extern "C" int sb_layernorm(const void* x, const void* res, void* y, void* sum_out, const float* w, const float* b,
+                            int32_t dim, int32_t batch, int32_t T, int32_t in_rows, int32_t in_halo, int32_t out_rows,
+                            int32_t out_halo, const int32_t* lens, int32_t mask_out, sb_stream_t stream) {
+  using namespace sb;
+  SB_REQUIRE(x && y && w && b && batch > 0 && T > 0, SB_EINVAL, "sb_layernorm: bad args");
+  SB_REQUIRE(dim % 8 == 0 && dim <= 256 * LN_MAX_CHUNKS, SB_ENOSUP, "sb_layernorm: dim %d unsupported (multiple of 8, <= 2048)", dim);
+  const long long rows = (long long)batch * T;
+  const int wpb = 8;
+  layernorm_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
+      (const elem_t*)x, (const elem_t*)res, (elem_t*)y, (elem_t*)sum_out, w, b, dim, rows, T, in_rows, in_halo, out_rows,
+      out_halo, lens, mask_out);
+  SB_LAUNCH_OK();
+  return SB_OK;
+}

@@ -1,0 +1,580 @@
+"""Host-side orchestration of the S2ST hot path on top of the C-ABI kernels.
+
+`UnitYEngine` holds the packed device weights of a UnitY2 model (speech encoder + adaptor, NLLB text decoder, NAR
+T2U) and sequences the kernels for each module of the path; `VocoderEngine` does the same for Code-HiFiGAN.
+Reference call stack being replaced: SURVEY.md 3.1 (inference/translator.py:216 -> inference/generator.py:228 ->
+models/unity/model.py / fairseq2 modules -> models/vocoder/*).
+
+Weight packing (one-time, at load):
+  * Linear weights stay (out,in) fp16 (K-major B operand of the tcgen05 GEMM); biases and LayerNorm params fp32;
+  * q/k/v projections are concatenated into one (3M,M) matrix; cross-attention k/v into (2M,M);
+  * Conv1d (out,in,k) -> (out,k,in) so that K index = tap*C_in + c matches the TMA tap walk;
+  * GLU-feeding weights are row-interleaved (a_j, b_j) so the GEMM epilogue can gate adjacent accumulator columns;
+  * HiFi-GAN weight_norm is folded (g*v/||v||), ConvTranspose1d becomes a 3-tap GEMM with stride*C_out outputs.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import _lib, ops
+from ._lib import BeamDesc, check
+from .config import UnitYConfig, VocoderConfig
+from .ops import ACT_LRELU, ACT_NONE, ACT_RELU, ACT_SILU, F16, Seq
+
+I32 = torch.int32
+
+
+def sinusoid_table(max_len: int, dim: int, legacy_pad_idx: int = 1) -> torch.Tensor:
+    """SinusoidalPositionEncoder table ([fs2-recall], oracle/ASSUMPTIONS.md #4; slice mirrored fairseq2.cpp:900-915)."""
+    half = dim // 2
+    steps = torch.arange(1 + legacy_pad_idx, 1 + legacy_pad_idx + max_len, dtype=torch.float32)
+    inv = torch.exp(torch.arange(half, dtype=torch.float32) * -(math.log(10000.0) / (half - 1)))
+    ang = steps[:, None] * inv[None, :]
+    return torch.cat([torch.sin(ang), torch.cos(ang)], dim=1).contiguous()
+
+
+def _interleave_glu(w: torch.Tensor) -> torch.Tensor:
+    """rows [a_0..a_{M-1}, b_0..b_{M-1}] -> [a_0, b_0, a_1, b_1, ...] (GLU(dim=channels) pairs adjacent)."""
+    M = w.shape[0] // 2
+    return torch.stack([w[:M], w[M:]], dim=1).reshape(w.shape).contiguous()
+
+
+class UnitYEngine:
+    def __init__(self, cfg: UnitYConfig, state_dict: Dict[str, torch.Tensor], tokenizers, device="cuda"):
+        _lib.require_cuda()
+        self.cfg = cfg
+        self.device = torch.device(device)
+        self.text_tokenizer, self.char_tokenizer = tokenizers
+        self.M, self.H = cfg.model_dim, cfg.num_heads
+        assert cfg.head_dim == 64, "attention kernels are specialised for head_dim 64"
+        self.has_t2u = any(k.startswith("t2u_model.") for k in state_dict)
+        self._pack(state_dict)
+        self.pos = sinusoid_table(cfg.max_seq_len, self.M).to(self.device)
+        if self.has_t2u:
+            self._build_char_tables()
+        self._graphs = {}
+
+    # ------------------------------------------------------------------------------------------ weight packing
+    def _pack(self, sd):
+        dev = self.device
+        w: Dict[str, torch.Tensor] = {}
+
+        def h(t):
+            return t.to(dev, F16).contiguous()
+
+        def f(t):
+            return t.to(dev, torch.float32).contiguous()
+
+        def lin(name):
+            w[name + ".w"] = h(sd[name + ".weight"])
+            if name + ".bias" in sd:
+                w[name + ".b"] = f(sd[name + ".bias"])
+
+        def ln(name):
+            w[name + ".w"], w[name + ".b"] = f(sd[name + ".weight"]), f(sd[name + ".bias"])
+
+        def conv(name, glu=False):
+            cw = sd[name + ".weight"].permute(0, 2, 1).reshape(sd[name + ".weight"].shape[0], -1)  # (out, k*in)
+            cb = sd.get(name + ".bias")
+            if glu:
+                cw = _interleave_glu(cw)
+                cb = _interleave_glu(cb) if cb is not None else None
+            w[name + ".w"] = h(cw)
+            if cb is not None:
+                w[name + ".b"] = f(cb)
+
+        def mha(name, fuse_qkv=True):
+            if fuse_qkv:
+                w[name + ".qkv.w"] = h(torch.cat([sd[f"{name}.{p}_proj.weight"] for p in "qkv"], 0))
+                w[name + ".qkv.b"] = f(torch.cat([sd[f"{name}.{p}_proj.bias"] for p in "qkv"], 0))
+            else:
+                lin(name + ".q_proj")
+                w[name + ".kv.w"] = h(torch.cat([sd[f"{name}.{p}_proj.weight"] for p in "kv"], 0))
+                w[name + ".kv.b"] = f(torch.cat([sd[f"{name}.{p}_proj.bias"] for p in "kv"], 0))
+            lin(name + ".output_proj")
+
+        c = self.cfg
+        ln("speech_encoder_frontend.post_extract_layer_norm")
+        lin("speech_encoder_frontend.model_dim_proj")
+        for i in range(c.enc_layers):
+            p = f"speech_encoder.inner.layers.{i}"
+            for n in ("ffn1", "ffn2"):
+                ln(f"{p}.{n}_layer_norm"); lin(f"{p}.{n}.inner_proj"); lin(f"{p}.{n}.output_proj")
+            ln(f"{p}.self_attn_layer_norm"); mha(f"{p}.self_attn")
+            w[f"{p}.rel_k"] = h(sd[f"{p}.self_attn.sdpa.rel_k_embed.weight"])
+            ln(f"{p}.conv_layer_norm")
+            conv(f"{p}.conv.pointwise_conv1", glu=True)
+            w[f"{p}.conv.dw.w"] = h(sd[f"{p}.conv.depthwise_conv.weight"].reshape(c.model_dim, c.dw_kernel))
+            ln(f"{p}.conv.layer_norm")
+            conv(f"{p}.conv.pointwise_conv2")
+            ln(f"{p}.layer_norm")
+        ln("speech_encoder.inner_layer_norm"); lin("speech_encoder.proj1"); lin("speech_encoder.proj2")
+        p = "speech_encoder.adaptor_layers.0"
+        ln(f"{p}.residual_layer_norm"); conv(f"{p}.residual_conv", glu=True)
+        ln(f"{p}.self_attn_layer_norm"); conv(f"{p}.self_attn_conv", glu=True)
+        mha(f"{p}.self_attn"); ln(f"{p}.ffn_layer_norm"); lin(f"{p}.ffn.inner_proj"); lin(f"{p}.ffn.output_proj")
+        ln("speech_encoder.layer_norm")
+        w["text_embed"] = h(sd["text_decoder_frontend.embed.weight"])  # tied with final_proj (builder.py:451)
+        for i in range(c.dec_layers):
+            p = f"text_decoder.layers.{i}"
+            ln(f"{p}.self_attn_layer_norm"); mha(f"{p}.self_attn")
+            ln(f"{p}.encoder_decoder_attn_layer_norm"); mha(f"{p}.encoder_decoder_attn", fuse_qkv=False)
+            ln(f"{p}.ffn_layer_norm"); lin(f"{p}.ffn.inner_proj"); lin(f"{p}.ffn.output_proj")
+        ln("text_decoder.layer_norm")
+        if self.has_t2u:
+            for i in range(c.t2u_enc_layers):
+                p = f"t2u_model.encoder.layers.{i}"
+                ln(f"{p}.self_attn_layer_norm"); mha(f"{p}.self_attn")
+                ln(f"{p}.ffn_layer_norm"); lin(f"{p}.ffn.inner_proj"); lin(f"{p}.ffn.output_proj")
+            ln("t2u_model.encoder.layer_norm")
+            P = "t2u_model.decoder_frontend"
+            w["unit_embed"] = h(sd[P + ".embed.weight"])
+            w["char_embed"] = h(sd[P + ".embed_char.weight"])
+            w["alpha"] = f(sd[P + ".pos_emb_alpha"]); w["alpha_char"] = f(sd[P + ".pos_emb_alpha_char"])
+            dp = P + ".variance_adaptor.duration_predictor"
+            conv(dp + ".conv1.0"); ln(dp + ".ln1"); conv(dp + ".conv2.0"); ln(dp + ".ln2")
+            w[dp + ".proj.w"] = h(sd[dp + ".proj.weight"].reshape(-1))
+            self.dur_bias = float(sd[dp + ".proj.bias"][0])
+            for i in range(c.t2u_dec_layers):
+                p = f"t2u_model.decoder.layers.{i}"
+                mha(f"{p}.self_attn"); ln(f"{p}.self_attn_layer_norm")
+                conv(f"{p}.conv1d.conv1"); conv(f"{p}.conv1d.conv2"); ln(f"{p}.conv1d_layer_norm")
+            ln("t2u_model.decoder.layer_norm")
+        self.w = w
+
+    def _build_char_tables(self):
+        """Per-token tables replacing the Python string loops of nar_decoder_frontend.py:130-259."""
+        tok, ctok = self.text_tokenizer, self.char_tokenizer
+        V = self.cfg.text_vocab
+        pieces = [tok.model.index_to_token(i) for i in range(V)]
+        max_chars = max(len(p) for p in pieces)
+        tl = torch.zeros(V, dtype=torch.uint8)
+        fl = torch.zeros(V, dtype=torch.uint8)
+        tc = torch.zeros(V, max_chars, dtype=torch.int32)
+        SP = "▁"
+        cache: Dict[str, int] = {}
+        for i, p in enumerate(pieces):
+            tl[i] = len(p)
+            punc = len(p) == 1 and not p.isalpha() and not p.isnumeric() and p != SP
+            nss = len(p) > 1 and p[0] == SP
+            fl[i] = int(punc) | (int(nss) << 1)
+            for j, ch in enumerate(p):
+                if ch not in cache:
+                    cache[ch] = ctok.model.token_to_index(ch)
+                tc[i, j] = cache[ch]
+        self.tok_len, self.tok_flags, self.tok_chars = tl.to(self.device), fl.to(self.device), tc.to(self.device)
+        self.max_chars = max_chars
+
+    # ------------------------------------------------------------------------------------------ building blocks
+    def _lin(self, x: Seq, name: str, n: int, **kw) -> Seq:
+        return ops.gemm(x, self.w[name + ".w"], n, self.w.get(name + ".b"), **kw)
+
+    def _ln(self, x: Seq, name: str, **kw) -> Seq:
+        return ops.layernorm(x, self.w[name + ".w"], self.w[name + ".b"], **kw)
+
+    def _mha_self(self, x_in: Seq, name: str, res: Seq, *, causal=False, rel=None) -> Seq:
+        M = self.M
+        qkv = self._lin(x_in, name + ".qkv", 3 * M)
+        c = self.cfg
+        a = ops.self_attention(qkv, self.H, causal=causal, rel_k=rel, rel_left=c.shaw_left if rel is not None else 0,
+                               rel_right=c.shaw_right if rel is not None else 0)
+        return self._lin(a, name + ".output_proj", M, res1=res)
+
+    def _ffn(self, x_in: Seq, name: str, inner: int, act: int, res: Seq, alpha=1.0) -> Seq:
+        t = self._lin(x_in, name + ".inner_proj", inner, act=act)
+        return self._lin(t, name + ".output_proj", self.M, res1=res, alpha=alpha)
+
+    # ------------------------------------------------------------------------------------------ a3-a6 speech encoder
+    def encode_speech(self, fbank: torch.Tensor, lens: Optional[torch.Tensor], return_inner=False):
+        """fbank (B, T_fb, 80) fp16 cuda, lens (B,) int32 cuda or None -> encoder output Seq (B, S_a, M), lens."""
+        c, M = self.cfg, self.M
+        B, T_fb, Cf = fbank.shape
+        s = c.fbank_stride
+        T2 = T_fb - (T_fb % s)
+        if T2 != T_fb:
+            fbank = fbank[:, :T2].contiguous()
+            lens = torch.clamp(lens, max=T2) if lens is not None else None
+        S = T2 // s
+        lens_s = (lens // s).to(I32) if lens is not None else None
+        x = Seq(B, S, Cf * s, lens=lens_s, buf=fbank.reshape(B * S, Cf * s))
+        x = self._ln(x, "speech_encoder_frontend.post_extract_layer_norm")
+        x = self._lin(x, "speech_encoder_frontend.model_dim_proj", M)
+        for i in range(c.enc_layers):
+            p = f"speech_encoder.inner.layers.{i}"
+            x = self._ffn(self._ln(x, p + ".ffn1_layer_norm"), p + ".ffn1", c.enc_ffn_dim, ACT_SILU, x, alpha=0.5)
+            x = self._mha_self(self._ln(x, p + ".self_attn_layer_norm"), p + ".self_attn", x, rel=self.w[p + ".rel_k"])
+            hcv = self._ln(x, p + ".conv_layer_norm", mask=True)
+            g = self._lin(hcv, p + ".conv.pointwise_conv1", 2 * M, glu=True)
+            d = ops.dwconv_ln_silu(g, self.w[p + ".conv.dw.w"], self.w[p + ".conv.layer_norm.w"],
+                                   self.w[p + ".conv.layer_norm.b"], c.dw_kernel)
+            x = self._lin(d, p + ".conv.pointwise_conv2", M, res1=x)
+            x = self._ffn(self._ln(x, p + ".ffn2_layer_norm"), p + ".ffn2", c.enc_ffn_dim, ACT_SILU, x, alpha=0.5)
+            x = self._ln(x, p + ".layer_norm")
+        inner = x
+        x = self._ln(x, "speech_encoder.inner_layer_norm")
+        t = self._lin(x, "speech_encoder.proj1", 4 * M, act=ACT_RELU)
+        x = self._lin(t, "speech_encoder.proj2", M, res1=x, alpha=0.5)
+        # adaptor layer (adaptor_block.py:236-314): Conv1d(k, stride k... here k == stride) as a reshaped GEMM
+        p = "speech_encoder.adaptor_layers.0"
+        k, st = c.adaptor_kernel, c.adaptor_stride
+        assert k == st, "adaptor conv is lowered to a reshape GEMM and needs kernel == stride"
+        S_a = S // st + 1
+        lens_a = (lens_s // st + 1).to(I32) if lens_s is not None else None
+
+        S_used = min(S, st * S_a - k // 2)  # frames past the last conv window are never read (floor in the length formula)
+        x_used = Seq(B, S_used, M, x.PH, x.Tp, lens_s, buf=x.buf)
+
+        def pooled(ln_name, conv_name):
+            padded = Seq(B, S_used, M, halo=k // 2, rows=st * S_a, lens=lens_s)  # left pad k//2, zero right pad
+            self._ln(x_used, ln_name, out=padded)
+            view = Seq(B, S_a, st * M, lens=lens_a, buf=padded.buf.view(B * S_a, st * M))
+            return ops.gemm(view, self.w[conv_name + ".w"], 2 * M, self.w[conv_name + ".b"], glu=True)
+
+        residual = pooled(p + ".residual_layer_norm", p + ".residual_conv")
+        hh = pooled(p + ".self_attn_layer_norm", p + ".self_attn_conv")
+        hh = self._mha_self(hh, p + ".self_attn", residual)
+        hh = self._ffn(self._ln(hh, p + ".ffn_layer_norm"), p + ".ffn", c.enc_ffn_dim, ACT_RELU, hh)
+        out = self._ln(hh, "speech_encoder.layer_norm")
+        return (out, lens_a, inner) if return_inner else (out, lens_a)
+
+    # ------------------------------------------------------------------------------------------ a7-a9 beam search
+    def _cross_kv(self, enc: Seq):
+        """per-utterance static cross-attention K/V for every decoder layer (computed once, not per beam)."""
+        return [self._lin(enc, f"text_decoder.layers.{i}.encoder_decoder_attn.kv", 2 * self.M)
+                for i in range(self.cfg.dec_layers)]
+
+    def _decoder_step_forward(self, st):
+        """One incremental decoder step for R rows; all shapes static, step index read from st['step'] on device.
+        The residual stream x is updated in place (the GEMM epilogue reads res1 and writes out element-wise)."""
+        lib = _lib.load()
+        c, M, H = self.cfg, self.M, self.H
+        R, stream = st["R"], ops._stream()
+        x = st["x"]
+        check(lib.sb_embed_step(st["seqs"].data_ptr(), st["ML"], st["step"].data_ptr(), self.w["text_embed"].data_ptr(),
+                                self.pos.data_ptr(), math.sqrt(M), x.buf.data_ptr(), R, M, stream), "sb_embed_step")
+        for i in range(c.dec_layers):
+            p = f"text_decoder.layers.{i}"
+            h = self._ln(x, p + ".self_attn_layer_norm", out=st["h"])
+            qkv = self._lin(h, p + ".self_attn.qkv", 3 * M, out=st["qkv"])
+            check(lib.sb_decode_self_attn(qkv.buf.data_ptr(), st["kc"][i].data_ptr(), st["vc"][i].data_ptr(),
+                                          st["anc"].data_ptr(), st["ML"], st["step"].data_ptr(), st["ML"],
+                                          st["att"].buf.data_ptr(), R, H, stream), "sb_decode_self_attn")
+            self._lin(st["att"], p + ".self_attn.output_proj", M, res1=x, out=x)
+            h = self._ln(x, p + ".encoder_decoder_attn_layer_norm", out=st["h"])
+            q = self._lin(h, p + ".encoder_decoder_attn.q_proj", M, out=st["q"])
+            kv = st["cross_kv"][i].buf
+            check(lib.sb_decode_cross_attn(q.buf.data_ptr(), kv.data_ptr(), kv[:, M:].data_ptr(), kv.stride(0),
+                                           ops._p(st["enc_lens"]), st["S_enc"], st["att"].buf.data_ptr(), R, st["beam"], H,
+                                           stream), "sb_decode_cross_attn")
+            self._lin(st["att"], p + ".encoder_decoder_attn.output_proj", M, res1=x, out=x)
+            h = self._ln(x, p + ".ffn_layer_norm", out=st["h"])
+            t = self._lin(h, p + ".ffn.inner_proj", c.dec_ffn_dim, act=ACT_RELU, out=st["ffn"])
+            self._lin(t, p + ".ffn.output_proj", M, res1=x, out=x)
+        h = self._ln(x, "text_decoder.layer_norm", out=st["h"])
+        ops.gemm(h, self.w["text_embed"], c.text_vocab, None, out=st["logits"], out_f32=True)
+
+    def _decoder_step_select(self, st):
+        lib = _lib.load()
+        c = self.cfg
+        stream = ops._stream()
+        check(lib.sb_logits_topk(st["logits"].buf.data_ptr(), st["logits"].buf.stride(0), st["R"], c.text_vocab, c.text_pad,
+                                 c.text_eos, c.text_unk, st["unk_penalty"], st["K"], st["cand_val"].data_ptr(),
+                                 st["cand_idx"].data_ptr(), st["eos_lprob"].data_ptr(), stream), "sb_logits_topk")
+        check(lib.sb_beam_step(C.byref(st["beam_desc"]), stream), "sb_beam_step")
+        check(lib.sb_step_advance(st["step"].data_ptr(), stream), "sb_step_advance")
+
+    def beam_search(self, enc: Seq, enc_lens, prefix: List[int], beam=5, soft_max=(1, 200), hard_max=1024,
+                    len_penalty=1.0, unk_penalty=0.0, min_seq_len=1, use_graph=True, cross_kv=None):
+        """Device-resident beam search.  Returns per sentence the finished hypotheses [(score, ids)], best first
+        (semantics: fairseq2.cpp:1371-1608; see decode.cu)."""
+        c, M, dev = self.cfg, self.M, self.device
+        B, S_enc = enc.B, enc.T
+        a, b = soft_max
+        ML = hard_max if a <= 0 else min(hard_max, int(a * S_enc) + b)  # fairseq2.cpp:1097-1105
+        P = len(prefix)
+        assert 1 <= P < ML
+        R = B * beam
+        K = min(2 * beam + 1, 16)
+        assert 2 * beam <= 16, "beam size above 8 is not supported by the top-K kernel"
+        st = dict(R=R, ML=ML, beam=beam, K=K, S_enc=S_enc, enc_lens=enc_lens, unk_penalty=float(unk_penalty))
+        st["cross_kv"] = cross_kv if cross_kv is not None else self._cross_kv(enc)
+        st["seqs"] = torch.zeros((R, ML), dtype=I32, device=dev)
+        st["seqs"][:, :P] = torch.tensor(prefix, dtype=I32, device=dev)
+        st["scores"] = torch.zeros((R, ML), dtype=torch.float32, device=dev)
+        st["anc"] = torch.arange(R, dtype=I32, device=dev)[:, None].repeat(1, ML).contiguous()
+        st["step"] = torch.zeros(1, dtype=I32, device=dev)
+        st["kc"] = [torch.empty((ML, R, M), dtype=F16, device=dev) for _ in range(c.dec_layers)]
+        st["vc"] = [torch.empty((ML, R, M), dtype=F16, device=dev) for _ in range(c.dec_layers)]
+        for name, width in (("x", M), ("h", M), ("q", M), ("att", M), ("qkv", 3 * M), ("ffn", c.dec_ffn_dim)):
+            st[name] = Seq(1, R, width)
+        st["logits"] = Seq(1, R, c.text_vocab, dtype=torch.float32, buf=torch.empty(
+            (R, (c.text_vocab + 7) // 8 * 8), dtype=torch.float32, device=dev))
+        st["cand_val"] = torch.empty((R, K), dtype=torch.float32, device=dev)
+        st["cand_idx"] = torch.empty((R, K), dtype=I32, device=dev)
+        st["eos_lprob"] = torch.empty((R,), dtype=torch.float32, device=dev)
+        fin = dict(count=torch.zeros(B, dtype=I32, device=dev), score=torch.full((B, beam), -math.inf, device=dev),
+                   len=torch.zeros((B, beam), dtype=I32, device=dev), seqs=torch.zeros((B, beam, ML), dtype=I32, device=dev),
+                   active=torch.ones(B, dtype=I32, device=dev), n_active=torch.full((1,), B, dtype=I32, device=dev))
+        d = BeamDesc()
+        d.batch, d.beam, d.max_len, d.vocab, d.K = B, beam, ML, c.text_vocab, K
+        d.step_ptr, d.prefix_len, d.eos_idx, d.min_len, d.len_penalty = st["step"].data_ptr(), P, c.text_eos, min_seq_len, len_penalty
+        d.cand_val, d.cand_idx, d.eos_lprob = st["cand_val"].data_ptr(), st["cand_idx"].data_ptr(), st["eos_lprob"].data_ptr()
+        d.seqs, d.scores, d.anc = st["seqs"].data_ptr(), st["scores"].data_ptr(), st["anc"].data_ptr()
+        d.fin_count, d.fin_score, d.fin_len = fin["count"].data_ptr(), fin["score"].data_ptr(), fin["len"].data_ptr()
+        d.fin_seqs, d.active, d.n_active = fin["seqs"].data_ptr(), fin["active"].data_ptr(), fin["n_active"].data_ptr()
+        st["beam_desc"] = d
+
+        def fwd():
+            self._decoder_step_forward(st)
+
+        g_fwd = g_sel = None
+        if use_graph:
+            # warm up once eagerly on a side stream (also initialises lazy state), then capture
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                fwd()
+            torch.cuda.current_stream().wait_stream(s)
+            g_fwd = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_fwd):
+                fwd()
+            g_sel = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_sel):
+                self._decoder_step_select(st)
+            # capture does not execute; state is untouched (step == 0, warm-up only wrote position-0 cache/buffers)
+
+        def run_fwd():
+            g_fwd.replay() if g_fwd is not None else fwd()
+
+        def run_sel():
+            g_sel.replay() if g_sel is not None else self._decoder_step_select(st)
+
+        # bootstrap (fairseq2.cpp:1162-1247): feed prefix[:-1], score prefix[1:]
+        lib = _lib.load()
+        for i in range(P - 1):
+            run_fwd()
+            # lprob of the next prefix token: the top-K kernel reports the lprob of its `eos_idx` argument
+            check(lib.sb_logits_topk(st["logits"].buf.data_ptr(), st["logits"].buf.stride(0), R, c.text_vocab, c.text_pad,
+                                     prefix[i + 1], c.text_unk, 0.0, K, st["cand_val"].data_ptr(), st["cand_idx"].data_ptr(),
+                                     st["eos_lprob"].data_ptr(), ops._stream()), "sb_logits_topk")
+            st["scores"][:, i + 1] = st["scores"][:, i] + st["eos_lprob"]
+            check(lib.sb_step_advance(st["step"].data_ptr(), ops._stream()), "sb_step_advance")
+        n_steps = ML - 1 - (P - 1)
+        done = 0
+        while done < n_steps:
+            chunk = min(16, n_steps - done)
+            for _ in range(chunk):
+                run_fwd()
+                run_sel()
+            done += chunk
+            if done < n_steps and int(fin["n_active"].item()) == 0:
+                break
+        cnt = fin["count"].cpu().tolist()
+        scr = fin["score"].cpu().tolist()
+        ln_ = fin["len"].cpu().tolist()
+        sq = fin["seqs"].cpu()
+        results = []
+        for bi in range(B):
+            hyps = [(scr[bi][j], sq[bi, j, :ln_[bi][j]].tolist()) for j in range(cnt[bi])]
+            order = sorted(range(len(hyps)), key=lambda j: -hyps[j][0])
+            results.append([hyps[j] for j in order])
+        self._last_search_state = st
+        return results
+
+    # ------------------------------------------------------------------------------------------ a10 teacher-forced pass
+    def decode_full(self, text_seqs: torch.Tensor, text_lens: torch.Tensor, enc: Seq, enc_lens, cross_kv=None) -> Seq:
+        """UnitYModel.decode without a state bag over (B, L) ids (generator.py:294-299)."""
+        c, M, H = self.cfg, self.M, self.H
+        B, L = text_seqs.shape
+        cross_kv = cross_kv if cross_kv is not None else self._cross_kv(enc)
+        xb = ops.embed_seq(text_seqs.to(I32).contiguous(), self.w["text_embed"], self.pos, math.sqrt(M), M)
+        x = Seq(B, L, M, lens=text_lens, buf=xb)
+        for i in range(c.dec_layers):
+            p = f"text_decoder.layers.{i}"
+            x = self._mha_self(self._ln(x, p + ".self_attn_layer_norm"), p + ".self_attn", x, causal=True)
+            h = self._ln(x, p + ".encoder_decoder_attn_layer_norm")
+            q = self._lin(h, p + ".encoder_decoder_attn.q_proj", M)
+            kv = cross_kv[i].buf
+            att = Seq(B, L, M)
+            ops.attention(q.buf, kv[:, :M], kv[:, M:], att.buf, B, H, L, enc.T, L, 0, enc.Tp, enc.PH, enc_lens)
+            x = self._lin(att, p + ".encoder_decoder_attn.output_proj", M, res1=x)
+            x = self._ffn(self._ln(x, p + ".ffn_layer_norm"), p + ".ffn", c.dec_ffn_dim, ACT_RELU, x)
+        return self._ln(x, "text_decoder.layer_norm")
+
+    # ------------------------------------------------------------------------------------------ a11-a14 NAR T2U
+    def t2u(self, dec_out: Seq, text_seqs: torch.Tensor, duration_factor: float = 1.0):
+        """UnitYNART2UModel.forward (model.py:379-402) + argmax/pad/UnitTokenDecoder (generator.py:338-353).
+        Returns units (B,U) int64 (pad -> 1 after decoding), unit_lens (B,), aux dict."""
+        lib = _lib.load()
+        c, M, dev = self.cfg, self.M, self.device
+        B, L = dec_out.B, dec_out.T
+        stream = ops._stream()
+        x = dec_out
+        for i in range(c.t2u_enc_layers):
+            p = f"t2u_model.encoder.layers.{i}"
+            x = self._mha_self(self._ln(x, p + ".self_attn_layer_norm"), p + ".self_attn", x)
+            x = self._ffn(self._ln(x, p + ".ffn_layer_norm"), p + ".ffn", c.t2u_ffn_dim, ACT_RELU, x)
+        t2u_enc = self._ln(x, "t2u_model.encoder.layer_norm")
+        # --- NARDecoderFrontend (nar_decoder_frontend.py:300-334)
+        ts = text_seqs.to(I32).contiguous()
+        max_c = (L - 2) * self.max_chars + 1 if L > 2 else 1
+        char_lens = torch.empty((B, L), dtype=I32, device=dev)
+        char_seqs = torch.empty((B, max_c), dtype=I32, device=dev)
+        char_seq_lens = torch.empty((B,), dtype=I32, device=dev)
+        check(lib.sb_text_to_chars(ts.data_ptr(), L, B, self.tok_len.data_ptr(), self.tok_flags.data_ptr(),
+                                   self.tok_chars.data_ptr(), self.max_chars, c.text_pad, c.text_unk, c.text_eos,
+                                   char_lens.data_ptr(), char_seqs.data_ptr(), max_c, char_seq_lens.data_ptr(), stream),
+              "sb_text_to_chars")
+        Cn = max(int(char_seq_lens.max().item()), 1)  # host sync #1 (the reference syncs here too: .item() at :231)
+        P = "t2u_model.decoder_frontend"
+        y = Seq(B, Cn, M, halo=1, lens=char_seq_lens)
+        check(lib.sb_upsample_add(t2u_enc.buf.data_ptr(), t2u_enc.Tp, t2u_enc.PH, L, char_lens.data_ptr(),
+                                  y.buf.data_ptr(), y.Tp, y.PH, Cn, B, M, self.pos.data_ptr(), self.w["alpha_char"].data_ptr(),
+                                  self.w["char_embed"].data_ptr(), char_seqs.data_ptr(), max_c, math.sqrt(M), None, stream),
+              "sb_upsample_add")
+        dp = P + ".variance_adaptor.duration_predictor"
+        h1 = ops.gemm(y, self.w[dp + ".conv1.0.w"], c.var_hidden, self.w[dp + ".conv1.0.b"], taps=c.var_kernel, act=ACT_RELU)
+        h1 = self._ln(h1, dp + ".ln1", mask=True)
+        h2 = ops.gemm(h1, self.w[dp + ".conv2.0.w"], c.var_hidden, self.w[dp + ".conv2.0.b"], taps=c.var_kernel, act=ACT_RELU)
+        h2 = self._ln(h2, dp + ".ln2", mask=True)
+        dur = torch.empty((B, Cn), dtype=I32, device=dev)
+        check(lib.sb_durations(h2.buf.data_ptr(), h2.Tp, h2.PH, self.w[dp + ".proj.w"].data_ptr(), self.dur_bias, c.var_hidden,
+                               char_seq_lens.data_ptr(), B, Cn, float(duration_factor), dur.data_ptr(), stream), "sb_durations")
+        unit_lens = dur.sum(dim=1).to(I32)
+        U = max(int(unit_lens.max().item()), 1)  # host sync #2 (reference: length_regulator.py:30)
+        halo = (c.fft_kernel - 1) // 2
+        z = Seq(B, U, M, halo=halo, lens=unit_lens)
+        check(lib.sb_upsample_add(y.buf.data_ptr(), y.Tp, y.PH, Cn, dur.data_ptr(), z.buf.data_ptr(), z.Tp, z.PH, U, B, M,
+                                  self.pos.data_ptr(), self.w["alpha"].data_ptr(), None, None, 0, 0.0, None, stream),
+              "sb_upsample_add")
+        # --- FeedForwardTransformer (fft_decoder.py:65-77, fft_decoder_layer.py:177-231)
+        for i in range(c.t2u_dec_layers):
+            p = f"t2u_model.decoder.layers.{i}"
+            s = self._mha_self(z, p + ".self_attn", z)
+            z1 = self._ln(s, p + ".self_attn_layer_norm", mask=True)
+            c1 = ops.gemm(z1, self.w[p + ".conv1d.conv1.w"], c.fft_inner_dim, self.w[p + ".conv1d.conv1.b"], taps=c.fft_kernel,
+                          act=ACT_RELU)
+            s2 = ops.gemm(c1, self.w[p + ".conv1d.conv2.w"], M, self.w[p + ".conv1d.conv2.b"], taps=c.fft_kernel, res1=z1)
+            z = self._ln(s2, p + ".conv1d_layer_norm", mask=True)
+        z = self._ln(z, "t2u_model.decoder.layer_norm", mask=True)
+        ldv = (c.unit_vocab + 7) // 8 * 8
+        logits = Seq(B, U, c.unit_vocab, z.PH, z.Tp, z.lens, dtype=torch.float32,
+                     buf=torch.empty((B * z.Tp, ldv), dtype=torch.float32, device=dev))
+        ops.gemm(z, self.w["unit_embed"], c.unit_vocab, None, out=logits, out_f32=True, mask=False)
+        units = torch.empty((B, U), dtype=I32, device=dev)
+        check(lib.sb_unit_argmax(logits.buf.data_ptr(), ldv, z.Tp, z.PH, U, B, c.unit_vocab, unit_lens.data_ptr(), c.unit_pad,
+                                 c.unit_eos, units.data_ptr(), stream), "sb_unit_argmax")
+        aux = dict(t2u_enc=t2u_enc, char_lens=char_lens, char_seqs=char_seqs[:, :Cn], char_seq_lens=char_seq_lens, dur=dur,
+                   fft_out=z, logits=logits)
+        return units.to(torch.int64), unit_lens, aux
+
+
+class VocoderEngine:
+    """Code-HiFiGAN (models/vocoder/{vocoder,codehifigan,hifigan}.py) on sb_gemm."""
+
+    HALO0 = 5  # unit-rate halo; scales with the upsampling so that stage 1 has the 25 rows k=11,d=5 needs
+
+    def __init__(self, cfg: VocoderConfig, state_dict: Dict[str, torch.Tensor], device="cuda"):
+        _lib.require_cuda()
+        self.cfg, self.device = cfg, torch.device(device)
+        self._pack(state_dict)
+
+    def _pack(self, sd):
+        dev, c = self.device, self.cfg
+        P = "code_generator."
+        w: Dict[str, torch.Tensor] = {}
+
+        def folded(name):  # weight_norm: w = g * v / ||v|| per dim-0 slice (hifigan.py:198-205 remove_weight_norm)
+            v, g = sd[P + name + ".weight_v"].float(), sd[P + name + ".weight_g"].float()
+            return g * v / v.flatten(1).norm(dim=1).view(-1, 1, 1)
+
+        def conv(name):
+            cw = folded(name)  # (out, in, k)
+            w[name + ".w"] = cw.permute(0, 2, 1).reshape(cw.shape[0], -1).to(dev, F16).contiguous()
+            w[name + ".b"] = sd[P + name + ".bias"].to(dev, torch.float32).contiguous()
+
+        for n in ("dict", "spkr", "lang"):
+            w[n] = sd[P + n + ".weight"].to(dev, F16).contiguous()
+        conv("conv_pre")
+        ch = c.upsample_initial_channel
+        for i, (u, k) in enumerate(zip(c.upsample_rates, c.upsample_kernel_sizes)):
+            cw = folded(f"ups.{i}")  # ConvTranspose1d weight (in, out, k)
+            cin, cout, pad = cw.shape[0], cw.shape[1], (k - u) // 2
+            wt = torch.zeros(u, cout, 3, cin)
+            for p in range(u):
+                for t in range(3):
+                    j = p + pad - (t - 1) * u
+                    if 0 <= j < k:
+                        wt[p, :, t, :] = cw[:, :, j].t()
+            w[f"ups.{i}.w"] = wt.reshape(u * cout, 3 * cin).to(dev, F16).contiguous()
+            w[f"ups.{i}.b"] = sd[P + f"ups.{i}.bias"].float().repeat(u).to(dev).contiguous()
+            for j in range(len(c.resblock_kernel_sizes)):
+                rb = i * len(c.resblock_kernel_sizes) + j
+                for d in range(len(c.resblock_dilation_sizes[j])):
+                    conv(f"resblocks.{rb}.convs1.{d}")
+                    conv(f"resblocks.{rb}.convs2.{d}")
+        cp = folded("conv_post")  # (1, C, 7)
+        w["conv_post.w"] = cp.permute(0, 2, 1).reshape(-1).to(dev, F16).contiguous()
+        self.conv_post_bias = float(sd[P + "conv_post.bias"][0])
+        self.w = w
+
+    def __call__(self, units: torch.Tensor, lang_idx: List[int], spkr_idx: List[int]) -> torch.Tensor:
+        """units (B,U) int -> waveform (B,1,U*hop) fp32  (CodeGenerator.forward with dur_prediction=False)."""
+        lib = _lib.load()
+        c, dev, w = self.cfg, self.device, self.w
+        B, U = units.shape
+        stream = ops._stream()
+        PH = self.HALO0
+        x0 = Seq(B, U, c.model_in_dim, halo=PH)
+        check(lib.sb_vocoder_embed(units.to(I32).contiguous().data_ptr(), U, B, w["dict"].data_ptr(), c.embedding_dim,
+                                   w["lang"].data_ptr(), c.lang_embedding_dim,
+                                   torch.tensor(lang_idx, dtype=I32, device=dev).data_ptr(), w["spkr"].data_ptr(),
+                                   c.spkr_embedding_dim, torch.tensor(spkr_idx, dtype=I32, device=dev).data_ptr(),
+                                   x0.buf.data_ptr(), x0.Tp, x0.PH, stream), "sb_vocoder_embed")
+        ch = c.upsample_initial_channel
+        act = ops.gemm(x0, w["conv_pre.w"], ch, w["conv_pre.b"], taps=7, act=ACT_LRELU, slope=0.1)  # lrelu fused for ups[0]
+        nk = len(c.resblock_kernel_sizes)
+        nstage = len(c.upsample_rates)
+        for i, u in enumerate(c.upsample_rates):
+            cout = ch // (2 ** (i + 1))
+            # ConvTranspose1d as a 3-tap GEMM producing u*cout values per input frame == u output frames of cout
+            up_raw = Seq(act.B, act.T, u * cout, act.PH, act.Tp)
+            up_act = Seq(act.B, act.T, u * cout, act.PH, act.Tp)
+            ops.gemm(act, w[f"ups.{i}.w"], u * cout, w[f"ups.{i}.b"], taps=3, out=up_raw, out2=up_act, out2_slope=0.1)
+            T, PHn, Tp = act.T * u, act.PH * u, act.Tp * u
+            x_raw = Seq(B, T, cout, PHn, Tp, buf=up_raw.buf.view(B * Tp, cout))
+            x_act = Seq(B, T, cout, PHn, Tp, buf=up_act.buf.view(B * Tp, cout))
+            last_slope = 0.01 if i == nstage - 1 else 0.1  # F.leaky_relu default slope before conv_post (hifigan.py:192)
+            xs = None
+            nxt_act = Seq(B, T, cout, PHn, Tp)
+            for j, (rk, dil) in enumerate(zip(c.resblock_kernel_sizes, c.resblock_dilation_sizes)):
+                rb = i * nk + j
+                y_raw, y_act = x_raw, x_act
+                for di, d in enumerate(dil):
+                    t1 = ops.gemm(y_act, w[f"resblocks.{rb}.convs1.{di}.w"], cout, w[f"resblocks.{rb}.convs1.{di}.b"], taps=rk,
+                                  dil=d, act=ACT_LRELU, slope=0.1)
+                    lastpair = di == len(dil) - 1
+                    if not lastpair:
+                        n_raw, n_act = Seq(B, T, cout, PHn, Tp), Seq(B, T, cout, PHn, Tp)
+                        ops.gemm(t1, w[f"resblocks.{rb}.convs2.{di}.w"], cout, w[f"resblocks.{rb}.convs2.{di}.b"], taps=rk,
+                                 res1=y_raw, out=n_raw, out2=n_act, out2_slope=0.1)
+                        y_raw, y_act = n_raw, n_act
+                    else:
+                        # xs (+)= resblock output; the last resblock also applies the 1/num_kernels mean and the
+                        # leaky-relu that feeds the next stage (hifigan.py:186-192)
+                        lastblock = j == nk - 1
+                        acc = Seq(B, T, cout, PHn, Tp)
+                        ops.gemm(t1, w[f"resblocks.{rb}.convs2.{di}.w"], cout, w[f"resblocks.{rb}.convs2.{di}.b"], taps=rk,
+                                 res1=y_raw, res2=xs, gamma=(1.0 / nk) if lastblock else 1.0, out=acc,
+                                 out2=nxt_act if lastblock else None, out2_slope=last_slope)
+                        xs = acc
+            act = nxt_act
+        Tw = act.T
+        wav = torch.empty((B, Tw), dtype=torch.float32, device=dev)
+        check(lib.sb_conv_post_tanh(act.buf.data_ptr(), act.Tp, act.PH, Tw, act.C, B, w["conv_post.w"].data_ptr(),
+                                    self.conv_post_bias, 7, wav.data_ptr(), wav.stride(0), stream), "sb_conv_post_tanh")
+        return wav.view(B, 1, Tw)
