@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""bench.py - S2ST utterances/sec for seamlessM4T_v2_large + vocoder_v2 on B200 (BASELINE.json metric).
+
+A "step" is one pass of the whole hot path (fbank -> Conformer encoder -> beam-search text decoder -> teacher-forced
+decoder pass -> NAR T2U -> Code-HiFiGAN) over one batch of 32 x 10 s synthetic 16 kHz utterances per GPU through
+`Translator.predict`, with random-init weights of the named architecture (no checkpoints are reachable offline).
+
+  value : utt/s with the input waveforms already resident in HBM when the timed region starts
+  e2e   : the same through the public API with HOST (pinned) waveforms -> H2D -> predict -> D2H of waveforms/units
+          (for N>1: rank 0 holds the global batch; NCCL scatter of waveforms, NCCL gather of results)
+  roofline      : the dominant kernel (tcgen05 GEMM) timed with CUDA events at its hottest shape (encoder FFN)
+  cpu_baseline  : the fp32 CPU oracle (a port of the reference path; the reference's fairseq2 stack is not
+                  installable offline) on a bounded sample, on this box's host cores
+  --impl reference : times that CPU path as the reference arm.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+TGT_LANG, LANG_IDX, SPKR_IDX = "spa", 25, 45
+BATCH, SAMPLES, HARD_MAX = 32, 160000, 102
+WORKLOAD = ("S2ST seamlessM4T_v2_large + vocoder_v2, batch 32x10s synthetic 16 kHz per GPU, beam 5, "
+            "hard_max_seq_len 102 (L=102 text tokens, U=495 units, 9.9 s out)")
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        pw = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm)}
+
+
+def build_models(device, keep_sd=False):
+    from seamless_communication_b200 import config as C, synthetic as S
+    from seamless_communication_b200.inference import Translator
+    from seamless_communication_b200.models.unity import load_unity_model
+    from seamless_communication_b200.models.vocoder import load_vocoder_model
+
+    cfg, vc = C.base_v2(), C.base_vocoder()
+    sd = S.make_unity_state_dict(cfg, seed=0, dec_gain=4.0)
+    vsd = S.make_vocoder_state_dict(vc, seed=1)
+    toks = S.make_tokenizers(cfg)
+    model = load_unity_model("seamlessM4T_v2_large", device=device, state_dict=sd, tokenizers=toks)
+    voc = load_vocoder_model("vocoder_v2", device=device, state_dict=vsd)
+    tr = Translator(model, voc, device=device)
+    return tr, (cfg, vc, sd if keep_sd else None, vsd if keep_sd else None, toks)
+
+
+def cpu_oracle_run(n_utts, threads):
+    """The reference CPU path (oracle port) on n_utts utterances of the bench workload; returns (seconds, utt/s)."""
+    from oracle.unity_oracle import UnityOracle, VocoderOracle, s2st
+    from seamless_communication_b200 import config as C, synthetic as S
+
+    torch.set_num_threads(threads)
+    cfg, vc = C.base_v2(), C.base_vocoder()
+    sd = S.make_unity_state_dict(cfg, seed=0, dec_gain=4.0)
+    vsd = S.make_vocoder_state_dict(vc, seed=1)
+    toks = S.make_tokenizers(cfg)
+    uo, vo = UnityOracle(cfg.to_dict(), sd, toks), VocoderOracle(vc.to_dict(), vsd)
+    waves = S.make_waveforms(n_utts, SAMPLES, seed=1234)
+    with torch.inference_mode():
+        t0 = time.time()
+        out = s2st(uo, vo, waves, TGT_LANG, LANG_IDX, SPKR_IDX, hard_max=HARD_MAX)
+        dt = time.time() - t0
+    return dt, n_utts / dt, out
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n = 1
+    for _ in range(args.warmup if args.warmup < 1 else 0):
+        pass
+    times = []
+    for _ in range(max(1, min(args.steps, 2))):  # bounded: each step is one utterance through the whole CPU path
+        dt, ups, _ = cpu_oracle_run(n, threads)
+        times.append(dt)
+    dt = statistics.mean(times)
+    v = n / dt
+    line = {"impl": "reference", "metric": "s2st_utterances_per_sec", "value": v, "unit": "utt/s", "n_gpus": args.gpus,
+            "steps": len(times), "warmup": 0, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "sample": f"{n} utterance per step on the host CPU"},
+            "cpu_baseline": {"value": v, "unit": "utt/s", "cores": threads, "kind": "port",
+                             "sample": f"{n} x 10 s utterance, full model, beam 5, L=102"},
+            "e2e": {"value": v, "unit": "utt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def time_dominant_gemm(tr):
+    """CUDA-event timing of the dominant kernel (gemm_tc_kernel<128>) at the encoder FFN shape."""
+    from seamless_communication_b200 import ops
+    from seamless_communication_b200.ops import Seq
+    M_rows, N, K = BATCH * 499, 4096, 1024
+    x = Seq(1, M_rows, K)
+    x.buf.normal_(0, 1)
+    w = tr.model.engine.w["speech_encoder.inner.layers.0.ffn1.inner_proj.w"]
+    b = tr.model.engine.w["speech_encoder.inner.layers.0.ffn1.inner_proj.b"]
+    out = Seq(1, M_rows, N)
+    for _ in range(5):
+        ops.gemm(x, w, N, b, act=ops.ACT_SILU, out=out)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 50
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        ops.gemm(x, w, N, b, act=ops.ACT_SILU, out=out)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    flops = 2.0 * M_rows * N * K
+    return ms, flops / (ms * 1e-3) / 1e12, f"gemm_tc_kernel<128> M={M_rows} N={N} K={K} (+bias+SiLU epilogue)"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--stages", action="store_true", help="also report per-stage GPU time")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    import torch.distributed as dist
+
+    from seamless_communication_b200 import ops, synthetic as S
+    from seamless_communication_b200.inference import SequenceGeneratorOptions
+
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    tr, _ = build_models(device)
+    opts = SequenceGeneratorOptions(beam_size=5, soft_max_seq_len=(1, 200), hard_max_seq_len=HARD_MAX)
+    waves_host = S.make_waveforms(BATCH, SAMPLES, seed=1234 + rank).pin_memory()
+    waves_dev = waves_host.to(device)
+
+    def step_device():
+        src = tr.fbank_batch(waves_dev)
+        return tr.predict(src, "s2st", TGT_LANG, text_generation_opts=opts)
+
+    # global batch on rank 0 for the e2e leg (scatter inputs / gather waveforms over NCCL)
+    if world > 1 and rank == 0:
+        global_host = torch.cat([S.make_waveforms(BATCH, SAMPLES, seed=1234 + r) for r in range(world)]).pin_memory()
+    h2d = d2h = 0
+
+    def step_e2e():
+        nonlocal h2d, d2h
+        if world > 1:
+            recv = torch.empty((BATCH, SAMPLES), dtype=torch.float32, device=device)
+            if rank == 0:
+                g = global_host.to(device, non_blocking=True)
+                dist.scatter(recv, list(g.chunk(world)), src=0)
+                h2d = global_host.numel() * 4
+            else:
+                dist.scatter(recv, None, src=0)
+            w = recv
+        else:
+            w = waves_host.to(device, non_blocking=True)
+            h2d = waves_host.numel() * 4
+        src = tr.fbank_batch(w)
+        texts, speech = tr.predict(src, "s2st", TGT_LANG, text_generation_opts=opts)
+        maxn = BATCH * 0 + max(x.shape[-1] for x in speech.audio_wavs)
+        wav = torch.zeros((BATCH, maxn), dtype=torch.float32, device=device)
+        for i, x in enumerate(speech.audio_wavs):
+            wav[i, :x.shape[-1]] = x[0, 0]
+        if world > 1:
+            # gather padded waveforms on rank 0 (fixed length for the fixed-length synthetic workload)
+            gathered = [torch.empty_like(wav) for _ in range(world)] if rank == 0 else None
+            dist.gather(wav, gathered, dst=0)
+            if rank == 0:
+                out = torch.cat(gathered).cpu()
+                d2h = out.numel() * 4
+        else:
+            out = wav.cpu()
+            d2h = out.numel() * 4 + sum(len(u) for u in speech.units) * 8
+        return texts
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        n0 = ops.launch_count() + tr.model.engine.graph_kernels
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = e0.elapsed_time(e1)
+        launches = ops.launch_count() + tr.model.engine.graph_kernels - n0
+        if world > 1:
+            t = torch.tensor([ms], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / steps, launches
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms_dev, launches = timed(step_device, args.steps, args.warmup)
+    clocks = sampler.stop() if sampler else None
+    ms_e2e, _ = timed(step_e2e, args.steps, 1)
+    value = world * BATCH / (ms_dev * 1e-3)
+    e2e_value = world * BATCH / (ms_e2e * 1e-3)
+
+    if rank == 0:
+        pk = peaks()
+        g_ms, g_tf, g_name = time_dominant_gemm(tr)
+        line = {
+            "metric": "s2st_utterances_per_sec", "value": value, "unit": "utt/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "per_gpu_batch": BATCH, "global_batch": BATCH * world, "parallelism": f"dp{world}",
+                       "l2": "working set (3.5 GB fp16 weights + activations) >> 126 MB L2, no explicit flush",
+                       "weights": "random-init, seeded", "accumulate": "f32"},
+            "rtf": ms_dev * 1e-3 / (10.0 * BATCH),
+            "e2e": {"value": e2e_value, "unit": "utt/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "kernel": g_name, "achieved": g_tf, "peak": pk["tf_burst"], "unit": "TFLOP/s",
+                         "frac": g_tf / pk["tf_burst"], "traffic": None, "peak_source": pk["src"] + " (burst, kernel timed alone)",
+                         "ms_per_launch": g_ms},
+            "clocks": clocks,
+        }
+        if args.stages:
+            line["stages_ms"] = stage_times(tr, waves_dev, opts)
+        if not args.no_cpu_baseline and world == 1:
+            threads = os.cpu_count() or 1
+            dt, ups, _ = cpu_oracle_run(1, threads)
+            line["cpu_baseline"] = {"value": ups, "unit": "utt/s", "cores": threads, "kind": "port",
+                                    "sample": "1 x 10 s utterance through the whole fp32 CPU oracle path (beam 5, L=102)",
+                                    "seconds": dt}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def stage_times(tr, waves_dev, opts):
+    """GPU time per stage of one step (CUDA events; development aid, not part of the timed region)."""
+    from seamless_communication_b200.ops import Seq
+    eng = tr.model.engine
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    marks = [ev() for _ in range(7)]
+    torch.cuda.synchronize()
+    marks[0].record()
+    src = tr.fbank_batch(waves_dev)
+    marks[1].record()
+    enc, lens = eng.encode_speech(src["seqs"], None)
+    marks[2].record()
+    prefix = [eng.cfg.text_eos, eng.text_tokenizer.lang_index(TGT_LANG)]
+    hyps = eng.beam_search(enc, None, prefix, beam=5, hard_max=HARD_MAX)
+    marks[3].record()
+    seqs = [h[0][1] for h in hyps]
+    L = max(len(s) for s in seqs)
+    ts = torch.zeros((len(seqs), L), dtype=torch.int64)
+    for i, s in enumerate(seqs):
+        ts[i, :len(s)] = torch.tensor(s)
+    ts = ts[:, :-1].contiguous().to(enc.buf.device)
+    tl = torch.tensor([len(s) - 1 for s in seqs], dtype=torch.int32, device=enc.buf.device)
+    dec = eng.decode_full(ts, tl, enc, None)
+    marks[4].record()
+    units, ulens, _ = eng.t2u(dec, ts)
+    marks[5].record()
+    tr.vocoder(units, TGT_LANG, -1, dur_prediction=False)
+    marks[6].record()
+    torch.cuda.synchronize()
+    names = ["fbank", "encoder", "beam_search", "redecode", "t2u", "vocoder"]
+    out = {n: marks[i].elapsed_time(marks[i + 1]) for i, n in enumerate(names)}
+    out["units_per_utt"] = int(ulens.max().item())
+    return out
+
+
+if __name__ == "__main__":
+    main()

@@ -181,7 +181,7 @@ def base_vocoder() -> VocoderConfig:
 def tiny_vocoder() -> VocoderConfig:
     return VocoderConfig(
         name="tiny",
-        upsample_initial_channel=64,
+        upsample_initial_channel=256,
         num_embeddings=256,
         embedding_dim=64,
         lang_embedding_dim=32,

@@ -29,13 +29,98 @@ __global__ void embed_kernel(const int* __restrict__ ids, long long ids_ld, cons
   }
 }
 
-// ------------------------------------------------------------------------------------------- self attention (1 token)
-// one warp per (row, head); 4 heads per CTA
+// ------------------------------------------------------------------------------------------- single-token attention
+// One warp per (row, head).  Lane l = (key group kg = l/8, dim chunk dc = l%8): every iteration the warp covers 4
+// keys with one 16-byte load per lane (128 B contiguous per key), so loads are independent and coalesced; scores
+// are reduced over the 8 lanes of a group with 3 shuffles, outputs over the 4 groups with 2.
+template <typename KeyPtr, typename ValPtr>
+__device__ __forceinline__ void attend_one(const elem_t* __restrict__ qp, int nkeys, KeyPtr kptr, ValPtr vptr, float* sc,
+                                           elem_t* __restrict__ outp) {
+  const int lane = threadIdx.x & 31, kg = lane >> 3, dc = lane & 7;
+  float q[8];
+  {
+    uint4 u = *reinterpret_cast<const uint4*>(qp + dc * 8);
+    const __half2* hh = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { float2 f = __half22float2(hh[e]); q[2 * e] = f.x; q[2 * e + 1] = f.y; }
+  }
+  float mx = -INFINITY;
+  // 16 keys per iteration: 4 independent 16-byte loads in flight per lane
+  for (int t0 = 0; t0 < nkeys; t0 += 16) {
+    uint4 u[4];
+    bool ok[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int t = t0 + 4 * i + kg;
+      ok[i] = t < nkeys;
+      u[i] = ok[i] ? *reinterpret_cast<const uint4*>(kptr(t) + dc * 8) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __half2* hh = reinterpret_cast<const __half2*>(&u[i]);
+      float acc = 0.f;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { float2 f = __half22float2(hh[e]); acc += q[2 * e] * f.x + q[2 * e + 1] * f.y; }
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+      acc *= 0.125f;
+      if (ok[i]) {
+        if (dc == 0) sc[t0 + 4 * i + kg] = acc;
+        mx = fmaxf(mx, acc);
+      }
+    }
+  }
+  mx = warp_max(mx);
+  __syncwarp();
+  float sum = 0.f;
+  for (int t = lane; t < nkeys; t += 32) {
+    const float p = __expf(sc[t] - mx);
+    sc[t] = p;
+    sum += p;
+  }
+  sum = warp_sum(sum);
+  __syncwarp();
+  float o[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) o[e] = 0.f;
+  for (int t0 = 0; t0 < nkeys; t0 += 16) {
+    uint4 u[4];
+    float pw[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int t = t0 + 4 * i + kg;
+      const bool ok = t < nkeys;
+      pw[i] = ok ? sc[t] : 0.f;
+      u[i] = ok ? *reinterpret_cast<const uint4*>(vptr(t) + dc * 8) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __half2* hh = reinterpret_cast<const __half2*>(&u[i]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { float2 f = __half22float2(hh[e]); o[2 * e] += pw[i] * f.x; o[2 * e + 1] += pw[i] * f.y; }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    o[e] += __shfl_xor_sync(0xffffffffu, o[e], 8);
+    o[e] += __shfl_xor_sync(0xffffffffu, o[e], 16);
+  }
+  if (kg == 0) {
+    const float inv = sum > 0.f ? 1.f / sum : 0.f;
+    uint4 u;
+    __half2* hh = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) hh[e] = __floats2half2_rn(o[2 * e] * inv, o[2 * e + 1] * inv);
+    *reinterpret_cast<uint4*>(outp + dc * 8) = u;
+  }
+}
+
 __global__ void __launch_bounds__(128) decode_self_attn_kernel(const elem_t* __restrict__ qkv, elem_t* __restrict__ kcache,
                                                                elem_t* __restrict__ vcache, const int* __restrict__ anc,
                                                                int anc_ld, const int* __restrict__ step_ptr, int max_len,
                                                                elem_t* __restrict__ out, int rows, int heads) {
-  extern __shared__ float sc_all[];  // [4][max_len]
+  extern __shared__ float sc_all[];  // [4][max_len] scores + [4][max_len] ancestor slots
   const int step = *step_ptr;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r = blockIdx.x;
@@ -43,6 +128,7 @@ __global__ void __launch_bounds__(128) decode_self_attn_kernel(const elem_t* __r
   if (h >= heads) return;
   const int dim = heads * HD;
   float* sc = sc_all + warp * max_len;
+  int* slots = reinterpret_cast<int*>(sc_all + 4 * max_len) + warp * max_len;
   const elem_t* qp = qkv + (long long)r * 3 * dim + h * HD;
   const elem_t* knew = qp + dim;
   const elem_t* vnew = qp + 2 * dim;
@@ -53,64 +139,24 @@ __global__ void __launch_bounds__(128) decode_self_attn_kernel(const elem_t* __r
     reinterpret_cast<__half2*>(kd)[lane] = reinterpret_cast<const __half2*>(knew)[lane];
     reinterpret_cast<__half2*>(vd)[lane] = reinterpret_cast<const __half2*>(vnew)[lane];
   }
-  float q[HD];
-#pragma unroll
-  for (int i = 0; i < HD / 8; ++i) {
-    uint4 u = *reinterpret_cast<const uint4*>(qp + i * 8);
-    const __half2* hh = reinterpret_cast<const __half2*>(&u);
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      float2 f = __half22float2(hh[e]);
-      q[i * 8 + 2 * e] = f.x;
-      q[i * 8 + 2 * e + 1] = f.y;
-    }
-  }
-  float mx = -INFINITY;
-  for (int t = lane; t <= step; t += 32) {
-    const elem_t* kp = (t == step) ? knew : kcache + ((long long)t * rows + anc[(long long)r * anc_ld + t]) * dim + h * HD;
-    float acc = 0.f;
-#pragma unroll
-    for (int i = 0; i < HD / 8; ++i) {
-      uint4 u = *reinterpret_cast<const uint4*>(kp + i * 8);
-      const __half2* hh = reinterpret_cast<const __half2*>(&u);
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        float2 f = __half22float2(hh[e]);
-        acc += q[i * 8 + 2 * e] * f.x + q[i * 8 + 2 * e + 1] * f.y;
-      }
-    }
-    acc *= 0.125f;
-    sc[t] = acc;
-    mx = fmaxf(mx, acc);
-  }
-  mx = warp_max(mx);
-  float sum = 0.f;
-  for (int t = lane; t <= step; t += 32) {
-    float p = __expf(sc[t] - mx);
-    sc[t] = p;
-    sum += p;
-  }
-  sum = warp_sum(sum);
+  for (int t = lane; t < step; t += 32) slots[t] = anc[(long long)r * anc_ld + t];
   __syncwarp();
-  float o0 = 0.f, o1 = 0.f;
-  for (int t = 0; t <= step; ++t) {
-    const elem_t* vp = (t == step) ? vnew : vcache + ((long long)t * rows + anc[(long long)r * anc_ld + t]) * dim + h * HD;
-    float2 f = __half22float2(reinterpret_cast<const __half2*>(vp)[lane]);
-    const float p = sc[t];
-    o0 += p * f.x;
-    o1 += p * f.y;
-  }
-  const float inv = 1.f / sum;
-  reinterpret_cast<__half2*>(out + (long long)r * dim + h * HD)[lane] = __floats2half2_rn(o0 * inv, o1 * inv);
+  const long long hoff = (long long)h * HD;
+  auto kptr = [&](int t) -> const elem_t* {
+    return (t == step) ? knew : kcache + ((long long)t * rows + slots[t]) * dim + hoff;
+  };
+  auto vptr = [&](int t) -> const elem_t* {
+    return (t == step) ? vnew : vcache + ((long long)t * rows + slots[t]) * dim + hoff;
+  };
+  attend_one(qp, step + 1, kptr, vptr, sc, out + (long long)r * dim + hoff);
 }
 
-// ------------------------------------------------------------------------------------------- cross attention (1 token)
 __global__ void __launch_bounds__(128) decode_cross_attn_kernel(const elem_t* __restrict__ q, const elem_t* __restrict__ k,
                                                                 const elem_t* __restrict__ v, long long kv_ld,
                                                                 const int* __restrict__ enc_lens, int s_enc,
                                                                 elem_t* __restrict__ out, int rows, int beam, int heads) {
   extern __shared__ float sc_all[];  // [4][s_enc]
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
   const int r = blockIdx.x;
   const int h = blockIdx.y * 4 + warp;
   if (h >= heads) return;
@@ -118,62 +164,28 @@ __global__ void __launch_bounds__(128) decode_cross_attn_kernel(const elem_t* __
   const int b = r / beam;
   const int len = enc_lens ? min(enc_lens[b], s_enc) : s_enc;
   float* sc = sc_all + warp * s_enc;
-  const elem_t* qp = q + (long long)r * dim + h * HD;
-  float qv[HD];
-#pragma unroll
-  for (int i = 0; i < HD / 8; ++i) {
-    uint4 u = *reinterpret_cast<const uint4*>(qp + i * 8);
-    const __half2* hh = reinterpret_cast<const __half2*>(&u);
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      float2 f = __half22float2(hh[e]);
-      qv[i * 8 + 2 * e] = f.x;
-      qv[i * 8 + 2 * e + 1] = f.y;
-    }
-  }
   const elem_t* kb = k + (long long)b * s_enc * kv_ld + h * HD;
   const elem_t* vb = v + (long long)b * s_enc * kv_ld + h * HD;
-  float mx = -INFINITY;
-  for (int t = lane; t < len; t += 32) {
-    const elem_t* kp = kb + (long long)t * kv_ld;
-    float acc = 0.f;
-#pragma unroll
-    for (int i = 0; i < HD / 8; ++i) {
-      uint4 u = *reinterpret_cast<const uint4*>(kp + i * 8);
-      const __half2* hh = reinterpret_cast<const __half2*>(&u);
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        float2 f = __half22float2(hh[e]);
-        acc += qv[i * 8 + 2 * e] * f.x + qv[i * 8 + 2 * e + 1] * f.y;
-      }
-    }
-    acc *= 0.125f;
-    sc[t] = acc;
-    mx = fmaxf(mx, acc);
-  }
-  mx = warp_max(mx);
-  float sum = 0.f;
-  for (int t = lane; t < len; t += 32) {
-    float p = __expf(sc[t] - mx);
-    sc[t] = p;
-    sum += p;
-  }
-  sum = warp_sum(sum);
-  __syncwarp();
-  float o0 = 0.f, o1 = 0.f;
-  for (int t = 0; t < len; ++t) {
-    float2 f = __half22float2(reinterpret_cast<const __half2*>(vb + (long long)t * kv_ld)[lane]);
-    const float p = sc[t];
-    o0 += p * f.x;
-    o1 += p * f.y;
-  }
-  const float inv = sum > 0.f ? 1.f / sum : 0.f;
-  reinterpret_cast<__half2*>(out + (long long)r * dim + h * HD)[lane] = __floats2half2_rn(o0 * inv, o1 * inv);
+  auto kptr = [&](int t) -> const elem_t* { return kb + (long long)t * kv_ld; };
+  auto vptr = [&](int t) -> const elem_t* { return vb + (long long)t * kv_ld; };
+  attend_one(q + (long long)r * dim + h * HD, len, kptr, vptr, sc, out + (long long)r * dim + h * HD);
 }
 
 // ------------------------------------------------------------------------------------------- log-softmax stats + top-K
+// One CTA per row, two streaming passes (the second one hits L2):
+//   pass 1: online max / sum-exp over the raw logits, plus each thread's single best candidate;
+//           tau = K-th largest of the per-thread bests is a lower bound of the K-th largest candidate overall;
+//   pass 2: every candidate >= tau (a few dozen at most, barring massive ties) is appended to a shared list;
+//   a single warp then extracts the top K in (value desc, index asc) order.
 constexpr int TK_MAX = 16;
 constexpr int TK_THREADS = 512;
+constexpr int TK_CAP = 2048;
+
+__device__ __forceinline__ float tk_cand(float x, int i, int pad_idx, int unk_idx, float unk_penalty) {
+  if (i == pad_idx) return -INFINITY;            // never allow PAD (fairseq2.cpp:1293-1296)
+  if (i == unk_idx) return x - unk_penalty;      // UNK penalty (fairseq2.cpp:1298-1305)
+  return x;
+}
 
 __global__ void __launch_bounds__(TK_THREADS) logits_topk_kernel(const float* __restrict__ logits, long long ld, int vocab,
                                                                  int pad_idx, int eos_idx, int unk_idx, float unk_penalty, int K,
@@ -181,84 +193,116 @@ __global__ void __launch_bounds__(TK_THREADS) logits_topk_kernel(const float* __
                                                                  float* __restrict__ eos_lprob) {
   const int r = blockIdx.x;
   const float* row = logits + (long long)r * ld;
-  float tv[TK_MAX];
-  int ti[TK_MAX];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __shared__ float s_m[TK_THREADS / 32], s_s[TK_THREADS / 32];
+  __shared__ float s_best[TK_THREADS];
+  __shared__ float s_lse, s_tau;
+  __shared__ int s_count;
+  __shared__ float s_cv[TK_CAP];
+  __shared__ int s_ci[TK_CAP];
+  const int nvec = vocab >> 2;
+  // ---- pass 1
+  float mx = -INFINITY, sum = 0.f, best = -INFINITY;
+  for (int i = threadIdx.x; i < nvec; i += TK_THREADS) {
+    const float4 v = *reinterpret_cast<const float4*>(row + 4 * i);
+    const float xs[4] = {v.x, v.y, v.z, v.w};
+    const float m4 = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+    if (m4 > mx) { sum *= __expf(mx - m4); mx = m4; }
 #pragma unroll
-  for (int i = 0; i < TK_MAX; ++i) { tv[i] = -INFINITY; ti[i] = 0x7fffffff; }
-  float mx = -INFINITY, sum = 0.f;
-  for (int i = threadIdx.x; i < vocab; i += TK_THREADS) {
+    for (int e = 0; e < 4; ++e) {
+      sum += __expf(xs[e] - mx);
+      best = fmaxf(best, tk_cand(xs[e], 4 * i + e, pad_idx, unk_idx, unk_penalty));
+    }
+  }
+  for (int i = 4 * nvec + threadIdx.x; i < vocab; i += TK_THREADS) {
     const float x = row[i];
-    // online softmax statistics over the raw logits
-    if (x > mx) { sum = sum * __expf(mx - x) + 1.f; mx = x; }
-    else sum += __expf(x - mx);
-    float cv = x;
-    if (i == pad_idx) cv = -INFINITY;
-    else if (i == unk_idx) cv = x - unk_penalty;
-    if (cv > tv[TK_MAX - 1] || (cv == tv[TK_MAX - 1] && i < ti[TK_MAX - 1])) {
-      // insertion into the sorted (descending, ties by lower index) per-thread list (keeps its best TK_MAX >= K)
-      float v = cv; int id = i;
+    if (x > mx) { sum *= __expf(mx - x); mx = x; }
+    sum += __expf(x - mx);
+    best = fmaxf(best, tk_cand(x, i, pad_idx, unk_idx, unk_penalty));
+  }
+  s_best[threadIdx.x] = best;
+  {
+    const float m2 = warp_max(mx);
+    const float s2 = warp_sum(mx == -INFINITY ? 0.f : sum * __expf(mx - m2));
+    if (lane == 0) { s_m[warp] = m2; s_s[warp] = s2; }
+  }
+  if (threadIdx.x == 0) s_count = 0;
+  __syncthreads();
+  if (warp == 0) {
+    float M = -INFINITY;
+    for (int i = 0; i < TK_THREADS / 32; ++i) M = fmaxf(M, s_m[i]);
+    float S = 0.f;
+    for (int i = 0; i < TK_THREADS / 32; ++i) S += s_s[i] * __expf(s_m[i] - M);
+    if (lane == 0) {
+      s_lse = M + logf(S);
+      eos_lprob[r] = row[eos_idx] - (M + logf(S));
+    }
+    // K-th largest of the 512 per-thread bests: each lane owns 16 of them
+    float loc[TK_THREADS / 32];
 #pragma unroll
-      for (int j = 0; j < TK_MAX; ++j) {
-        if (v > tv[j] || (v == tv[j] && id < ti[j])) {
-          float t1 = tv[j]; int t2 = ti[j];
-          tv[j] = v; ti[j] = id; v = t1; id = t2;
-        }
+    for (int i = 0; i < TK_THREADS / 32; ++i) loc[i] = s_best[lane * (TK_THREADS / 32) + i];
+    float tau = -INFINITY;
+    for (int round = 0; round < K; ++round) {
+      float lm = -INFINITY; int li = 0;
+#pragma unroll
+      for (int i = 0; i < TK_THREADS / 32; ++i) if (loc[i] > lm) { lm = loc[i]; li = i; }
+      const float wm = warp_max(lm);
+      tau = wm;
+      // the first lane holding the maximum removes one copy
+      const unsigned ball = __ballot_sync(0xffffffffu, lm == wm);
+      if (lane == __ffs(ball) - 1) {
+#pragma unroll
+        for (int i = 0; i < TK_THREADS / 32; ++i) if (i == li) loc[i] = -INFINITY;
+      }
+    }
+    if (lane == 0) s_tau = tau;
+  }
+  __syncthreads();
+  const float tau = s_tau, lse = s_lse;
+  // ---- pass 2: gather candidates >= tau
+  for (int i = threadIdx.x; i < nvec; i += TK_THREADS) {
+    const float4 v = *reinterpret_cast<const float4*>(row + 4 * i);
+    const float xs[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float cv = tk_cand(xs[e], 4 * i + e, pad_idx, unk_idx, unk_penalty);
+      if (cv >= tau && cv > -INFINITY) {
+        const int slot = atomicAdd(&s_count, 1);
+        if (slot < TK_CAP) { s_cv[slot] = cv; s_ci[slot] = 4 * i + e; }
       }
     }
   }
-  // block reduction of (max, sum)
-  __shared__ float s_m[TK_THREADS / 32], s_s[TK_THREADS / 32];
-  __shared__ float s_bv[TK_THREADS / 32];
-  __shared__ int s_bi[TK_THREADS / 32], s_bt[TK_THREADS / 32];
-  __shared__ float s_lse;
-  __shared__ int s_win_thread;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  {
-    float m2 = warp_max(mx);
-    float s2 = warp_sum(sum * __expf(mx - m2));
-    if (lane == 0) { s_m[warp] = m2; s_s[warp] = s2; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      float M = -INFINITY;
-      for (int i = 0; i < TK_THREADS / 32; ++i) M = fmaxf(M, s_m[i]);
-      float S = 0.f;
-      for (int i = 0; i < TK_THREADS / 32; ++i) S += s_s[i] * __expf(s_m[i] - M);
-      s_lse = M + logf(S);
-      eos_lprob[r] = row[eos_idx] - s_lse;
+  for (int i = 4 * nvec + threadIdx.x; i < vocab; i += TK_THREADS) {
+    const float cv = tk_cand(row[i], i, pad_idx, unk_idx, unk_penalty);
+    if (cv >= tau && cv > -INFINITY) {
+      const int slot = atomicAdd(&s_count, 1);
+      if (slot < TK_CAP) { s_cv[slot] = cv; s_ci[slot] = i; }
     }
-    __syncthreads();
   }
-  const float lse = s_lse;
-  // K rounds: pick the best head among all threads' sorted lists
-  for (int round = 0; round < K; ++round) {
-    float v = tv[0];
-    int id = ti[0];
-    int th = threadIdx.x;
+  __syncthreads();
+  // ---- top-K of the candidate list, one warp
+  if (warp == 0) {
+    const int n = min(s_count, TK_CAP);
+    for (int round = 0; round < K; ++round) {
+      float bv = -INFINITY; int bi = 0x7fffffff, bs = -1;
+      for (int j = lane; j < n; j += 32) {
+        const float v = s_cv[j]; const int id = s_ci[j];
+        if (v > bv || (v == bv && id < bi)) { bv = v; bi = id; bs = j; }
+      }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      float v2 = __shfl_xor_sync(0xffffffffu, v, o);
-      int id2 = __shfl_xor_sync(0xffffffffu, id, o);
-      int th2 = __shfl_xor_sync(0xffffffffu, th, o);
-      if (v2 > v || (v2 == v && id2 < id)) { v = v2; id = id2; th = th2; }
+      for (int o = 16; o > 0; o >>= 1) {
+        const float v2 = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int i2 = __shfl_xor_sync(0xffffffffu, bi, o);
+        const int s2 = __shfl_xor_sync(0xffffffffu, bs, o);
+        if (v2 > bv || (v2 == bv && i2 < bi)) { bv = v2; bi = i2; bs = s2; }
+      }
+      if (lane == 0) {
+        cand_val[(long long)r * K + round] = bs >= 0 ? bv - lse : -INFINITY;
+        cand_idx[(long long)r * K + round] = bs >= 0 ? bi : 0;
+        if (bs >= 0) s_cv[bs] = -INFINITY;
+      }
+      __syncwarp();
     }
-    if (lane == 0) { s_bv[warp] = v; s_bi[warp] = id; s_bt[warp] = th; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      float bv = s_bv[0]; int bi = s_bi[0], bt = s_bt[0];
-      for (int i = 1; i < TK_THREADS / 32; ++i)
-        if (s_bv[i] > bv || (s_bv[i] == bv && s_bi[i] < bi)) { bv = s_bv[i]; bi = s_bi[i]; bt = s_bt[i]; }
-      cand_val[(long long)r * K + round] = bv - lse;
-      cand_idx[(long long)r * K + round] = bi;
-      s_win_thread = bt;
-    }
-    __syncthreads();
-    if (threadIdx.x == s_win_thread) {
-      // pop the head of the winner's list (shift left)
-#pragma unroll
-      for (int j = 0; j < TK_MAX - 1; ++j) { tv[j] = tv[j + 1]; ti[j] = ti[j + 1]; }
-      tv[TK_MAX - 1] = -INFINITY; ti[TK_MAX - 1] = 0x7fffffff;
-    }
-    __syncthreads();
   }
 }
 
@@ -386,7 +430,7 @@ extern "C" int sb_decode_self_attn(const void* qkv, void* kcache, void* vcache, 
   using namespace sb;
   SB_REQUIRE(qkv && kcache && vcache && anc && out && step_ptr && rows > 0 && heads > 0 && max_len > 0, SB_EINVAL,
              "sb_decode_self_attn: bad args");
-  size_t smem = (size_t)4 * max_len * sizeof(float);
+  size_t smem = (size_t)8 * max_len * sizeof(float);
   SB_REQUIRE(smem <= 48 * 1024, SB_ENOSUP, "sb_decode_self_attn: max_len %d too large", max_len);
   decode_self_attn_kernel<<<dim3(rows, (heads + 3) / 4), 128, smem, (cudaStream_t)stream>>>(
       (const elem_t*)qkv, (elem_t*)kcache, (elem_t*)vcache, anc, anc_ld, step_ptr, max_len, (elem_t*)out, rows, heads);

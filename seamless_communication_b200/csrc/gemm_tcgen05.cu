@@ -4,14 +4,19 @@
 //   TMEM, issued by one thread) -> tcgen05.ld epilogue (bias, activation / GLU, residuals, sequence mask, fp16|fp32
 //   store, optional leaky-relu'd second output).
 //
-// Warp roles (192 threads): warps 0-3 epilogue (TMEM lane quarter = warp id), warp 4 TMA producer, warp 5 MMA issuer
-// + TMEM allocator.  One 128 x BN output tile per CTA; 2 CTAs co-reside per SM (<= 96 KB smem, <= 128 TMEM columns
-// each) so one CTA's epilogue overlaps the other's main loop.
+// Warp roles: warps 0-3 epilogue (TMEM lane quarter = warp id), warp 4 MMA issuer + TMEM allocator, warps 5.. TMA
+// producers - ONE PRODUCER PER PIPELINE STAGE.  Measured on B200 (tools/tma_probe.py, profiles/r01_tma_probe.txt):
+// a single thread sustains only one wait-empty / expect-tx / cp.async.bulk.tensor round per ~650 cycles no matter
+// how many stages are in flight, so a lone producer caps a CTA at ~25 B/clk; one producer per stage multiplies that.
+// One 128 x BN output tile per CTA; 2 CTAs co-reside per SM (<= 96 KB smem, <= 128 TMEM columns each) so one CTA's
+// epilogue overlaps the other's main loop.  The epilogue stages the tile in shared memory (128B-swizzled, conflict
+// free) and writes it with TMA bulk stores (full 128 B rows; tile tails are clipped by the tensor map).
 //
 // Conv taps are realised purely through the TMA row coordinate: tap j of output row m reads A row
 // a_row0 + m + j*dil, the weight K index is j*c_in + c.  Rows outside [0, a_rows) and channels >= c_in are
 // zero-filled by TMA, so c_in need not be a multiple of 64.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -41,6 +46,7 @@ struct GemmArgs {
   long long out_row0;
   int seq_rows, seq_halo, seq_len;
   const int* seq_lens;
+  int tma_store;  // epilogue through smem + cp.async.bulk.tensor stores
 };
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
@@ -125,11 +131,23 @@ struct TileCfg {
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
   static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + BN * 4;
+  static constexpr int THREADS = 32 * (5 + STAGES);
+  // epilogue staging reuses the (drained) pipeline stages: out groups first, out2 groups after them
+  static constexpr int OUT_GROUPS_MAX = BN * 4 / 128;  // fp32 worst case: 32 columns per 16 KB group
+  static constexpr int OUT2_OFFSET = OUT_GROUPS_MAX * 16384;
+  static_assert(OUT2_OFFSET + (BN / 64 > 0 ? BN / 64 : 1) * 16384 <= STAGES * STAGE_BYTES, "staging does not fit");
 };
 
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+
 template <int BN>
-__global__ void __launch_bounds__(192, (BN >= 128) ? 2 : 2)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmArgs g) {
+__global__ void __launch_bounds__(TileCfg<BN>::THREADS, 2)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+               const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmO2, const GemmArgs g) {
   using Cfg = TileCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -154,7 +172,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     mbar_init(tmem_full_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 5) {  // TMEM allocation (whole warp), address lands in smem
+  if (warp == 4) {  // TMEM allocation (whole warp), address lands in smem
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
                  "r"((uint32_t)Cfg::TMEM_COLS)
                  : "memory");
@@ -171,40 +189,41 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  if (warp == 4) {
-    // ------------------------------------------------------------------ TMA producer
+  if (warp >= 5) {
+    // ------------------------------------------------------------------ TMA producers: warp 5+s owns stage s
     if (lane == 0) {
-      for (int kb = 0; kb < kblocks; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
+      const int s = warp - 5;
+      uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
+      uint32_t ph = 0;
+      for (int kb = s; kb < kblocks; kb += STAGES, ph ^= 1) {
         mbar_wait(&empty_bar[s], ph ^ 1);
         mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
         const int tap = kb / cblocks, c0 = (kb - tap * cblocks) * BK;
-        uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
         tma_load_2d(sa, &tmA, &full_bar[s], c0, m0 + g.a_row0 + tap * g.dil);
         tma_load_2d(sa + A_TILE_BYTES, &tmW, &full_bar[s], tap * g.c_in + c0, n0);
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 4) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       // instruction descriptor: D=f32, A=B=f16 (0) / bf16 (1), K-major both, N>>3, M>>4
       const uint32_t idesc = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      int s = 0, cb = 0;
+      uint32_t ph = 0;
       for (int kb = 0; kb < kblocks; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES);
         const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + A_TILE_BYTES);
-        const int tap = kb / cblocks, c0 = (kb - tap * cblocks) * BK;
-        int ksteps = (g.c_in - c0 + 15) / 16;
+        int ksteps = (g.c_in - cb * BK + 15) >> 4;
         if (ksteps > BK / 16) ksteps = BK / 16;
+        if (++cb == cblocks) cb = 0;
         for (int k = 0; k < ksteps; ++k) {
           // advance 16 elements (32 B) along K inside the swizzle atom: +2 in the (addr >> 4) field
           tc_mma_f16(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
         }
         tc_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
+        if (++s == STAGES) { s = 0; ph ^= 1; }
       }
       tc_commit(tmem_full_bar);    // accumulator complete
     }
@@ -218,6 +237,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const long long q = m + g.out_row0;
     const bool valid = row_ok && seq_row_valid(q, g.seq_rows, g.seq_halo, g.seq_len, g.seq_lens);
     const int n_out_total = g.glu ? g.n / 2 : g.n;
+    // NOTE: every access to v[] below uses compile-time indices (fully unrolled loops with predicates); a single
+    // runtime-indexed access would push the whole array to local memory (seen in profiles/r01_gemm_v1_*.txt).
+    const bool has_res = valid && (g.res1 != nullptr || g.res2 != nullptr);
+    const float post_scale = has_res ? g.gamma : g.alpha * g.gamma;
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       if (n0 + c0 >= g.n) break;  // warp-uniform
@@ -231,98 +254,158 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int oc = n0 + c0;    // first output column
       if (g.glu) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = v[2 * j] / (1.f + __expf(-v[2 * j + 1]));
+        for (int j = 0; j < 16; ++j) v[j] = __fdividef(v[2 * j], 1.f + __expf(-v[2 * j + 1]));
         nv = 16;
         oc = (n0 + c0) >> 1;
-      } else if (g.act != SB_ACT_NONE) {
+      } else if (g.act == SB_ACT_RELU) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], g.act, g.act_slope);
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+      } else if (g.act == SB_ACT_SILU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __fdividef(v[j], 1.f + __expf(-v[j]));
+      } else if (g.act == SB_ACT_LRELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * g.act_slope;
+      } else if (g.act == SB_ACT_TANH) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
       }
       const bool full = (oc + nv <= n_out_total);
-      // residuals
-      if (valid && (g.res1 != nullptr || g.res2 != nullptr)) {
+      if (has_res) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] *= g.alpha;
-        const elem_t* rp[2] = {g.res1, g.res2};
-        const long long rl[2] = {g.res1_ld, g.res2_ld};
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
-          if (rp[t] == nullptr) continue;
-          const elem_t* p = rp[t] + q * rl[t] + oc;
-          if (full && ((rl[t] | oc) & 7) == 0) {
-            for (int j = 0; j < nv; j += 8) {
-              uint4 u = *reinterpret_cast<const uint4*>(p + j);
-              const __half2* h = reinterpret_cast<const __half2*>(&u);
+          const elem_t* rp = t == 0 ? g.res1 : g.res2;
+          const long long rl = t == 0 ? g.res1_ld : g.res2_ld;
+          if (rp == nullptr) continue;
+          const elem_t* p = rp + q * rl + oc;
+          if (full && ((rl | oc) & 7) == 0) {
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                float2 f = __half22float2(h[e]);
-                v[j + 2 * e] += f.x;
-                v[j + 2 * e + 1] += f.y;
+            for (int j8 = 0; j8 < 4; ++j8) {
+              if (8 * j8 < nv) {
+                const uint4 u = *reinterpret_cast<const uint4*>(p + 8 * j8);
+                const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 f = __half22float2(h[e]);
+                  v[8 * j8 + 2 * e] += f.x;
+                  v[8 * j8 + 2 * e + 1] += f.y;
+                }
               }
             }
           } else {
-            for (int j = 0; j < nv; ++j)
-              if (oc + j < n_out_total) v[j] += __half2float(p[j]);
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < nv && oc + j < n_out_total) v[j] += __half2float(p[j]);
           }
         }
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] *= g.gamma;
-      } else {
-        const float sc = g.alpha * g.gamma;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] *= sc;
       }
-      if (!valid) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = 0.f;
-      }
+      for (int j = 0; j < 32; ++j) v[j] = valid ? v[j] * post_scale : 0.f;
       // stores
+      if (g.tma_store) {
+        // stage into shared memory: 16 KB groups of [128 rows][128 B], 16-byte chunk index XOR (row & 7) (SWIZZLE_128B)
+        const int rsw = row & 7;
+        const int oc_local = g.glu ? (c0 >> 1) : c0;  // first output column of this chunk inside the tile
+        if (g.out_f32) {
+          uint8_t* gb = smem + (oc_local >> 5) * 16384 + row * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(gb + ((j ^ rsw) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        } else {
+          uint8_t* gb = smem + (oc_local >> 6) * 16384 + row * 128;
+          const int cb = (oc_local & 63) >> 3;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (8 * j < nv) {
+              uint4 u;
+              __half2* h = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(v[8 * j + 2 * e], v[8 * j + 2 * e + 1]);
+              *reinterpret_cast<uint4*>(gb + (((cb + j) ^ rsw) << 4)) = u;
+            }
+          }
+        }
+        if (g.out2 != nullptr) {
+          uint8_t* gb = smem + Cfg::OUT2_OFFSET + (oc_local >> 6) * 16384 + row * 128;
+          const int cb = (oc_local & 63) >> 3;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (8 * j < nv) {
+              uint4 u;
+              __half2* h = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float a = v[8 * j + 2 * e], b = v[8 * j + 2 * e + 1];
+                h[e] = __floats2half2_rn(a > 0.f ? a : a * g.out2_slope, b > 0.f ? b : b * g.out2_slope);
+              }
+              *reinterpret_cast<uint4*>(gb + (((cb + j) ^ rsw) << 4)) = u;
+            }
+          }
+        }
+        continue;
+      }
+      // direct (per-thread row) stores: small tiles / unaligned outputs
       if (g.out_f32) {
         float* p = reinterpret_cast<float*>(g.out) + q * g.out_ld + oc;
         if (full && ((g.out_ld | oc) & 3) == 0) {
-          for (int j = 0; j < nv; j += 4) *reinterpret_cast<float4*>(p + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (4 * j < nv) *reinterpret_cast<float4*>(p + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         } else {
-          for (int j = 0; j < nv; ++j)
-            if (oc + j < n_out_total) p[j] = v[j];
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < nv && oc + j < n_out_total) p[j] = v[j];
         }
       } else {
         elem_t* p = reinterpret_cast<elem_t*>(g.out) + q * g.out_ld + oc;
         if (full && ((g.out_ld | oc) & 7) == 0) {
-          for (int j = 0; j < nv; j += 8) {
-            uint4 u;
-            __half2* h = reinterpret_cast<__half2*>(&u);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(v[j + 2 * e], v[j + 2 * e + 1]);
-            *reinterpret_cast<uint4*>(p + j) = u;
+          for (int j = 0; j < 4; ++j) {
+            if (8 * j < nv) {
+              uint4 u;
+              __half2* h = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(v[8 * j + 2 * e], v[8 * j + 2 * e + 1]);
+              *reinterpret_cast<uint4*>(p + 8 * j) = u;
+            }
           }
         } else {
-          for (int j = 0; j < nv; ++j)
-            if (oc + j < n_out_total) p[j] = __float2half_rn(v[j]);
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < nv && oc + j < n_out_total) p[j] = __float2half_rn(v[j]);
         }
       }
       if (g.out2 != nullptr) {
         elem_t* p = g.out2 + q * g.out2_ld + oc;
-        if (full && ((g.out2_ld | oc) & 7) == 0) {
-          for (int j = 0; j < nv; j += 8) {
-            uint4 u;
-            __half2* h = reinterpret_cast<__half2*>(&u);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float a = v[j + 2 * e], b = v[j + 2 * e + 1];
-              h[e] = __floats2half2_rn(a > 0.f ? a : a * g.out2_slope, b > 0.f ? b : b * g.out2_slope);
-            }
-            *reinterpret_cast<uint4*>(p + j) = u;
-          }
-        } else {
-          for (int j = 0; j < nv; ++j)
-            if (oc + j < n_out_total) p[j] = __float2half_rn(v[j] > 0.f ? v[j] : v[j] * g.out2_slope);
-        }
+        for (int j = 0; j < 32; ++j)
+          if (j < nv && oc + j < n_out_total) p[j] = __float2half_rn(v[j] > 0.f ? v[j] : v[j] * g.out2_slope);
+      }
+    }
+    if (g.tma_store) {
+      // make the staged tile visible to the async proxy, then one thread issues the bulk tensor stores
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (threadIdx.x == 0) {
+        const int n_tile_out = g.glu ? BN / 2 : BN;
+        const int oc0 = g.glu ? (n0 >> 1) : n0;
+        const int q0 = (int)(m0 + g.out_row0);
+        const int gcols = g.out_f32 ? 32 : 64;
+        for (int c = 0; c < n_tile_out; c += gcols)
+          if (oc0 + c < n_out_total) tma_store_2d(&tmO, smem + (c / gcols) * 16384, oc0 + c, q0);
+        if (g.out2 != nullptr)
+          for (int c = 0; c < n_tile_out; c += 64)
+            if (oc0 + c < n_out_total) tma_store_2d(&tmO2, smem + Cfg::OUT2_OFFSET + (c / 64) * 16384, oc0 + c, q0);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 4) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS)
                  : "memory");
@@ -346,20 +429,20 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// 2D fp16 tensor (inner = channels, outer = rows), box 64 x box_rows, 128B swizzle, OOB -> 0
+// 2D tensor (inner = channels, outer = rows), box box_cols x box_rows (box_cols * esize = 128 B), 128B swizzle, OOB -> 0
 static int make_tmap(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t rows, uint64_t ld_elems,
-                     uint32_t box_rows) {
+                     uint32_t box_rows, int esize = 2) {
   EncodeTiledFn fn = get_encode_fn();
   SB_REQUIRE(fn != nullptr, SB_ECUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[2] = {inner, rows};
-  cuuint64_t strides[1] = {ld_elems * 2};
-  cuuint32_t box[2] = {BK, box_rows};
+  cuuint64_t strides[1] = {ld_elems * (uint64_t)esize};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / esize), box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  SB_REQUIRE(r == CUDA_SUCCESS, SB_ECUDA, "cuTensorMapEncodeTiled failed (%d): inner=%llu rows=%llu ld=%llu", (int)r,
-             (unsigned long long)inner, (unsigned long long)rows, (unsigned long long)ld_elems);
+  CUresult r = fn(tm, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                  const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SB_REQUIRE(r == CUDA_SUCCESS, SB_ECUDA, "cuTensorMapEncodeTiled failed (%d): inner=%llu rows=%llu ld=%llu esize=%d", (int)r,
+             (unsigned long long)inner, (unsigned long long)rows, (unsigned long long)ld_elems, esize);
   return SB_OK;
 }
 
@@ -383,6 +466,7 @@ static void fill_args(const sb_gemm_t* g, GemmArgs* a) {
   a->out2 = (elem_t*)g->out2; a->out2_ld = g->out2_ld; a->out2_slope = g->out2_slope;
   a->out_row0 = g->out_row0;
   a->seq_rows = g->seq_rows; a->seq_halo = g->seq_halo; a->seq_len = g->seq_len; a->seq_lens = g->seq_lens;
+  a->tma_store = 0;
 }
 
 template <int BN>
@@ -393,15 +477,39 @@ static int launch(const sb_gemm_t* g, cudaStream_t st) {
     SB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;
   }
-  CUtensorMap tmA, tmW;
+  CUtensorMap tmA, tmW, tmO, tmO2;
   int rc = make_tmap(&tmA, g->a, (uint64_t)g->c_in, (uint64_t)g->a_rows, (uint64_t)g->a_ld, BM);
   if (rc) return rc;
   rc = make_tmap(&tmW, g->w, (uint64_t)g->taps * g->c_in, (uint64_t)g->n, (uint64_t)g->taps * g->c_in, BN);
   if (rc) return rc;
   GemmArgs args;
   fill_args(g, &args);
+  // staged TMA-store epilogue needs 128 B output groups (64 fp16 / 32 fp32 columns) and 16 B aligned rows
+  const int esize = g->out_f32 ? 4 : 2;
+  const int n_tile_out = g->glu ? BN / 2 : BN;
+  const int n_out_total = g->glu ? g->n / 2 : g->n;
+  bool tma_ok = n_tile_out * esize >= 128 && ((uintptr_t)g->out % 16) == 0 && ((g->out_ld * esize) % 16) == 0 &&
+                g->out_row0 >= 0 && (g->out_row0 + g->m) < (1ll << 31) && !(g->glu && g->out_f32);
+  if (g->out2 != nullptr) tma_ok = tma_ok && ((uintptr_t)g->out2 % 16) == 0 && ((g->out2_ld * 2) % 16) == 0 && n_tile_out >= 64;
+  static int force_direct = -1;
+  if (force_direct < 0) { const char* e = getenv("SB_GEMM_DIRECT_STORE"); force_direct = e ? atoi(e) : 0; }
+  if (force_direct) tma_ok = false;
+  if (tma_ok) {
+    rc = make_tmap(&tmO, g->out, (uint64_t)n_out_total, (uint64_t)(g->out_row0 + g->m), (uint64_t)g->out_ld, BM, esize);
+    if (rc) return rc;
+    if (g->out2 != nullptr) {
+      rc = make_tmap(&tmO2, g->out2, (uint64_t)n_out_total, (uint64_t)(g->out_row0 + g->m), (uint64_t)g->out2_ld, BM, 2);
+      if (rc) return rc;
+    } else {
+      tmO2 = tmO;
+    }
+    args.tma_store = 1;
+  } else {
+    tmO = tmA;
+    tmO2 = tmA;
+  }
   dim3 grid((g->n + BN - 1) / BN, (g->m + BM - 1) / BM);
-  gemm_tc_kernel<BN><<<grid, 192, Cfg::SMEM_BYTES, st>>>(tmA, tmW, args);
+  gemm_tc_kernel<BN><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmW, tmO, tmO2, args);
   SB_LAUNCH_OK();
   return SB_OK;
 }

@@ -57,6 +57,7 @@ class UnitYEngine:
         if self.has_t2u:
             self._build_char_tables()
         self._graphs = {}
+        self.graph_kernels = 0  # kernels executed through CUDA-graph replays (bench.py: gpu_launches)
 
     # ------------------------------------------------------------------------------------------ weight packing
     def _pack(self, sd):
@@ -189,6 +190,7 @@ class UnitYEngine:
         return self._lin(t, name + ".output_proj", self.M, res1=res, alpha=alpha)
 
     # ------------------------------------------------------------------------------------------ a3-a6 speech encoder
+    @torch.inference_mode()
     def encode_speech(self, fbank: torch.Tensor, lens: Optional[torch.Tensor], return_inner=False):
         """fbank (B, T_fb, 80) fp16 cuda, lens (B,) int32 cuda or None -> encoder output Seq (B, S_a, M), lens."""
         c, M = self.cfg, self.M
@@ -287,25 +289,25 @@ class UnitYEngine:
         check(lib.sb_beam_step(C.byref(st["beam_desc"]), stream), "sb_beam_step")
         check(lib.sb_step_advance(st["step"].data_ptr(), stream), "sb_step_advance")
 
-    def beam_search(self, enc: Seq, enc_lens, prefix: List[int], beam=5, soft_max=(1, 200), hard_max=1024,
-                    len_penalty=1.0, unk_penalty=0.0, min_seq_len=1, use_graph=True, cross_kv=None):
-        """Device-resident beam search.  Returns per sentence the finished hypotheses [(score, ids)], best first
-        (semantics: fairseq2.cpp:1371-1608; see decode.cu)."""
+    def _search_state(self, B, S_enc, ML, beam, P, has_lens, use_graph):
+        """Static buffers + captured CUDA graphs of one decoder step, cached per problem shape so that repeated
+        predict() calls replay the same graphs (the reference rebuilds its generator per call, translator.py:179-186;
+        construction here stays cheap after the first call)."""
+        key = (B, S_enc, ML, beam, P, has_lens, use_graph)
+        st = self._graphs.get(key)
+        if st is not None:
+            return st
         c, M, dev = self.cfg, self.M, self.device
-        B, S_enc = enc.B, enc.T
-        a, b = soft_max
-        ML = hard_max if a <= 0 else min(hard_max, int(a * S_enc) + b)  # fairseq2.cpp:1097-1105
-        P = len(prefix)
-        assert 1 <= P < ML
         R = B * beam
         K = min(2 * beam + 1, 16)
         assert 2 * beam <= 16, "beam size above 8 is not supported by the top-K kernel"
-        st = dict(R=R, ML=ML, beam=beam, K=K, S_enc=S_enc, enc_lens=enc_lens, unk_penalty=float(unk_penalty))
-        st["cross_kv"] = cross_kv if cross_kv is not None else self._cross_kv(enc)
+        st = dict(R=R, ML=ML, beam=beam, K=K, S_enc=S_enc, B=B, P=P, unk_penalty=0.0)
+        st["enc_lens"] = torch.zeros(B, dtype=I32, device=dev) if has_lens else None
+        st["cross_kv"] = [Seq(B, S_enc, 2 * M) for _ in range(c.dec_layers)]
         st["seqs"] = torch.zeros((R, ML), dtype=I32, device=dev)
-        st["seqs"][:, :P] = torch.tensor(prefix, dtype=I32, device=dev)
         st["scores"] = torch.zeros((R, ML), dtype=torch.float32, device=dev)
-        st["anc"] = torch.arange(R, dtype=I32, device=dev)[:, None].repeat(1, ML).contiguous()
+        st["anc"] = torch.zeros((R, ML), dtype=I32, device=dev)
+        st["anc_init"] = torch.arange(R, dtype=I32, device=dev)[:, None].repeat(1, ML).contiguous()
         st["step"] = torch.zeros(1, dtype=I32, device=dev)
         st["kc"] = [torch.empty((ML, R, M), dtype=F16, device=dev) for _ in range(c.dec_layers)]
         st["vc"] = [torch.empty((ML, R, M), dtype=F16, device=dev) for _ in range(c.dec_layers)]
@@ -316,42 +318,95 @@ class UnitYEngine:
         st["cand_val"] = torch.empty((R, K), dtype=torch.float32, device=dev)
         st["cand_idx"] = torch.empty((R, K), dtype=I32, device=dev)
         st["eos_lprob"] = torch.empty((R,), dtype=torch.float32, device=dev)
-        fin = dict(count=torch.zeros(B, dtype=I32, device=dev), score=torch.full((B, beam), -math.inf, device=dev),
+        fin = dict(count=torch.zeros(B, dtype=I32, device=dev), score=torch.zeros((B, beam), device=dev),
                    len=torch.zeros((B, beam), dtype=I32, device=dev), seqs=torch.zeros((B, beam, ML), dtype=I32, device=dev),
-                   active=torch.ones(B, dtype=I32, device=dev), n_active=torch.full((1,), B, dtype=I32, device=dev))
+                   active=torch.ones(B, dtype=I32, device=dev), n_active=torch.zeros((1,), dtype=I32, device=dev))
+        st["fin"] = fin
         d = BeamDesc()
         d.batch, d.beam, d.max_len, d.vocab, d.K = B, beam, ML, c.text_vocab, K
-        d.step_ptr, d.prefix_len, d.eos_idx, d.min_len, d.len_penalty = st["step"].data_ptr(), P, c.text_eos, min_seq_len, len_penalty
+        d.step_ptr, d.prefix_len, d.eos_idx = st["step"].data_ptr(), P, c.text_eos
         d.cand_val, d.cand_idx, d.eos_lprob = st["cand_val"].data_ptr(), st["cand_idx"].data_ptr(), st["eos_lprob"].data_ptr()
         d.seqs, d.scores, d.anc = st["seqs"].data_ptr(), st["scores"].data_ptr(), st["anc"].data_ptr()
         d.fin_count, d.fin_score, d.fin_len = fin["count"].data_ptr(), fin["score"].data_ptr(), fin["len"].data_ptr()
         d.fin_seqs, d.active, d.n_active = fin["seqs"].data_ptr(), fin["active"].data_ptr(), fin["n_active"].data_ptr()
         st["beam_desc"] = d
+        st["g_fwd"] = st["g_sel"] = None
+        st["n_fwd"] = st["n_sel"] = 0
+        self._graphs[key] = st
+        return st
 
-        def fwd():
+    def _capture(self, st):
+        """Capture the forward and the select halves of a decoder step (all pointers/shapes static)."""
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):  # eager warm-up: lazy one-time initialisation must not happen during capture
             self._decoder_step_forward(st)
+            self._decoder_step_select(st)
+        torch.cuda.current_stream().wait_stream(s)
+        n0 = ops.launch_count()
+        st["g_fwd"] = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(st["g_fwd"]):
+            self._decoder_step_forward(st)
+        n1 = ops.launch_count()
+        st["g_sel"] = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(st["g_sel"]):
+            self._decoder_step_select(st)
+        st["n_fwd"], st["n_sel"] = n1 - n0, ops.launch_count() - n1
 
-        g_fwd = g_sel = None
-        if use_graph:
-            # warm up once eagerly on a side stream (also initialises lazy state), then capture
-            s = torch.cuda.Stream()
-            s.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(s):
-                fwd()
-            torch.cuda.current_stream().wait_stream(s)
-            g_fwd = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g_fwd):
-                fwd()
-            g_sel = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g_sel):
-                self._decoder_step_select(st)
-            # capture does not execute; state is untouched (step == 0, warm-up only wrote position-0 cache/buffers)
+    @torch.inference_mode()
+    def beam_search(self, enc: Seq, enc_lens, prefix: List[int], beam=5, soft_max=(1, 200), hard_max=1024,
+                    len_penalty=1.0, unk_penalty=0.0, min_seq_len=1, use_graph=True, cross_kv=None):
+        """Device-resident beam search.  Returns per sentence the finished hypotheses [(score, ids)], best first
+        (semantics: fairseq2.cpp:1371-1608; see decode.cu).  `cross_kv` is ignored (kept for API stability): the
+        static cross-attention K/V of the cached search state are recomputed from `enc`."""
+        c, M, dev = self.cfg, self.M, self.device
+        B, S_enc = enc.B, enc.T
+        a, b = soft_max
+        ML = hard_max if a <= 0 else min(hard_max, int(a * S_enc) + b)  # fairseq2.cpp:1097-1105
+        P = len(prefix)
+        assert 1 <= P < ML
+        st = self._search_state(B, S_enc, ML, beam, P, enc_lens is not None, use_graph)
+        R, K, fin = st["R"], st["K"], st["fin"]
+        # (re)initialise the search state in place
+        st["unk_penalty"] = float(unk_penalty)
+        d = st["beam_desc"]
+        if (d.min_len, d.len_penalty) != (min_seq_len, len_penalty) or st.get("unk_cap") != float(unk_penalty):
+            d.min_len, d.len_penalty = min_seq_len, len_penalty
+            st["g_fwd"] = st["g_sel"] = None  # scalar options are baked into the captured select graph
+            st["unk_cap"] = float(unk_penalty)
+        if enc_lens is not None:
+            st["enc_lens"].copy_(enc_lens)
+        for i in range(c.dec_layers):
+            self._lin(enc, f"text_decoder.layers.{i}.encoder_decoder_attn.kv", 2 * M, out=st["cross_kv"][i])
+        st["seqs"].zero_()
+        st["seqs"][:, :P] = torch.tensor(prefix, dtype=I32, device=dev)
+        st["scores"].zero_()
+        st["anc"].copy_(st["anc_init"])
+        fin["count"].zero_(); fin["score"].fill_(-math.inf); fin["len"].zero_(); fin["active"].fill_(1)
+        fin["n_active"].fill_(B)
+        if use_graph and st["g_fwd"] is None:
+            st["step"].zero_()
+            self._capture(st)
+            # the warm-up touched position-0 cache rows and the search state: reset what it changed
+            st["seqs"].zero_()
+            st["seqs"][:, :P] = torch.tensor(prefix, dtype=I32, device=dev)
+            st["scores"].zero_()
+            st["anc"].copy_(st["anc_init"])
+            fin["count"].zero_(); fin["score"].fill_(-math.inf); fin["len"].zero_(); fin["active"].fill_(1)
+            fin["n_active"].fill_(B)
+        st["step"].zero_()
 
         def run_fwd():
-            g_fwd.replay() if g_fwd is not None else fwd()
+            if use_graph:
+                st["g_fwd"].replay(); self.graph_kernels += st["n_fwd"]
+            else:
+                self._decoder_step_forward(st)
 
         def run_sel():
-            g_sel.replay() if g_sel is not None else self._decoder_step_select(st)
+            if use_graph:
+                st["g_sel"].replay(); self.graph_kernels += st["n_sel"]
+            else:
+                self._decoder_step_select(st)
 
         # bootstrap (fairseq2.cpp:1162-1247): feed prefix[:-1], score prefix[1:]
         lib = _lib.load()
@@ -366,7 +421,7 @@ class UnitYEngine:
         n_steps = ML - 1 - (P - 1)
         done = 0
         while done < n_steps:
-            chunk = min(16, n_steps - done)
+            chunk = min(32, n_steps - done)
             for _ in range(chunk):
                 run_fwd()
                 run_sel()
@@ -382,15 +437,19 @@ class UnitYEngine:
             hyps = [(scr[bi][j], sq[bi, j, :ln_[bi][j]].tolist()) for j in range(cnt[bi])]
             order = sorted(range(len(hyps)), key=lambda j: -hyps[j][0])
             results.append([hyps[j] for j in order])
+        st["enc_ptr"] = enc.buf.data_ptr()
         self._last_search_state = st
         return results
 
     # ------------------------------------------------------------------------------------------ a10 teacher-forced pass
+    @torch.inference_mode()
     def decode_full(self, text_seqs: torch.Tensor, text_lens: torch.Tensor, enc: Seq, enc_lens, cross_kv=None) -> Seq:
         """UnitYModel.decode without a state bag over (B, L) ids (generator.py:294-299)."""
         c, M, H = self.cfg, self.M, self.H
         B, L = text_seqs.shape
-        cross_kv = cross_kv if cross_kv is not None else self._cross_kv(enc)
+        if cross_kv is None:
+            st = getattr(self, "_last_search_state", None)
+            cross_kv = st["cross_kv"] if (st is not None and st.get("enc_ptr") == enc.buf.data_ptr()) else self._cross_kv(enc)
         xb = ops.embed_seq(text_seqs.to(I32).contiguous(), self.w["text_embed"], self.pos, math.sqrt(M), M)
         x = Seq(B, L, M, lens=text_lens, buf=xb)
         for i in range(c.dec_layers):
@@ -406,7 +465,9 @@ class UnitYEngine:
         return self._ln(x, "text_decoder.layer_norm")
 
     # ------------------------------------------------------------------------------------------ a11-a14 NAR T2U
-    def t2u(self, dec_out: Seq, text_seqs: torch.Tensor, duration_factor: float = 1.0):
+    @torch.inference_mode()
+    def t2u(self, dec_out: Seq, text_seqs: torch.Tensor, duration_factor: float = 1.0,
+            durations: Optional[torch.Tensor] = None):
         """UnitYNART2UModel.forward (model.py:379-402) + argmax/pad/UnitTokenDecoder (generator.py:338-353).
         Returns units (B,U) int64 (pad -> 1 after decoding), unit_lens (B,), aux dict."""
         lib = _lib.load()
@@ -444,6 +505,8 @@ class UnitYEngine:
         dur = torch.empty((B, Cn), dtype=I32, device=dev)
         check(lib.sb_durations(h2.buf.data_ptr(), h2.Tp, h2.PH, self.w[dp + ".proj.w"].data_ptr(), self.dur_bias, c.var_hidden,
                                char_seq_lens.data_ptr(), B, Cn, float(duration_factor), dur.data_ptr(), stream), "sb_durations")
+        if durations is not None:  # VarianceAdaptor.forward(durations=...) override (length_regulator.py:275-283)
+            dur = durations.to(device=dev, dtype=I32).contiguous()
         unit_lens = dur.sum(dim=1).to(I32)
         U = max(int(unit_lens.max().item()), 1)  # host sync #2 (reference: length_regulator.py:30)
         halo = (c.fft_kernel - 1) // 2
@@ -522,6 +585,7 @@ class VocoderEngine:
         self.conv_post_bias = float(sd[P + "conv_post.bias"][0])
         self.w = w
 
+    @torch.inference_mode()
     def __call__(self, units: torch.Tensor, lang_idx: List[int], spkr_idx: List[int]) -> torch.Tensor:
         """units (B,U) int -> waveform (B,1,U*hop) fp32  (CodeGenerator.forward with dur_prediction=False)."""
         lib = _lib.load()
@@ -530,11 +594,15 @@ class VocoderEngine:
         stream = ops._stream()
         PH = self.HALO0
         x0 = Seq(B, U, c.model_in_dim, halo=PH)
-        check(lib.sb_vocoder_embed(units.to(I32).contiguous().data_ptr(), U, B, w["dict"].data_ptr(), c.embedding_dim,
-                                   w["lang"].data_ptr(), c.lang_embedding_dim,
-                                   torch.tensor(lang_idx, dtype=I32, device=dev).data_ptr(), w["spkr"].data_ptr(),
-                                   c.spkr_embedding_dim, torch.tensor(spkr_idx, dtype=I32, device=dev).data_ptr(),
-                                   x0.buf.data_ptr(), x0.Tp, x0.PH, stream), "sb_vocoder_embed")
+        # NOTE: every tensor whose data_ptr() is handed to a kernel must stay referenced until after the launch;
+        # a temporary freed earlier can be re-issued by the caching allocator to the next allocation.
+        units_i = units.to(I32).contiguous()
+        lang_t = torch.tensor(lang_idx, dtype=I32, device=dev)
+        spkr_t = torch.tensor(spkr_idx, dtype=I32, device=dev)
+        check(lib.sb_vocoder_embed(units_i.data_ptr(), U, B, w["dict"].data_ptr(), c.embedding_dim,
+                                   w["lang"].data_ptr(), c.lang_embedding_dim, lang_t.data_ptr(), w["spkr"].data_ptr(),
+                                   c.spkr_embedding_dim, spkr_t.data_ptr(), x0.buf.data_ptr(), x0.Tp, x0.PH, stream),
+              "sb_vocoder_embed")
         ch = c.upsample_initial_channel
         act = ops.gemm(x0, w["conv_pre.w"], ch, w["conv_pre.b"], taps=7, act=ACT_LRELU, slope=0.1)  # lrelu fused for ups[0]
         nk = len(c.resblock_kernel_sizes)

@@ -92,10 +92,8 @@ class UnitYGenerator:
         enc = Seq(B, S, M, buf=enc_out.view(B * S, M))
         enc_lens = None if enc_mask is None else enc_mask.seq_lens.to(device=enc_out.device, dtype=I32)
         o = self.text_opts
-        cross_kv = eng._cross_kv(enc)
         hyps = eng.beam_search(enc, enc_lens, self.prefix, beam=o.beam_size, soft_max=o.soft_max_seq_len,
-                               hard_max=o.hard_max_seq_len, len_penalty=o.len_penalty, unk_penalty=o.unk_penalty,
-                               cross_kv=cross_kv)
+                               hard_max=o.hard_max_seq_len, len_penalty=o.len_penalty, unk_penalty=o.unk_penalty)
         for h in hyps:
             if not h:
                 raise RuntimeError("The sequence generator returned no hypothesis at index 0. Please file a bug report.")
@@ -112,7 +110,7 @@ class UnitYGenerator:
             text_seqs[i, :len(s)] = torch.tensor(s)
         text_seqs = text_seqs[:, :-1].contiguous().to(enc_out.device)  # "trim the final EOS" (generator.py:287)
         text_lens = torch.tensor([len(s) - 1 for s in text_seq_list], dtype=I32, device=enc_out.device)
-        dec = eng.decode_full(text_seqs, text_lens, enc, enc_lens, cross_kv=cross_kv)  # generator.py:294-299
+        dec = eng.decode_full(text_seqs, text_lens, enc, enc_lens)  # generator.py:294-299
         assert self.model.t2u_model is not None and self.unit_decoder is not None
         units, unit_lens, aux = eng.t2u(dec, text_seqs, duration_factor)
         # engine.t2u already applied argmax -> pad mask -> UnitTokenDecoder (generator.py:346-353) on device

@@ -201,7 +201,59 @@ def stage_vocoder():
     print("vocoder wav", tuple(wav.shape), f"max abs err {(wav.float().cpu() - ref).abs().max().item():.3e} (std {ref.std().item():.3f})")
 
 
-STAGES = dict(gemm=stage_gemm, fbank=stage_fbank, ln=stage_ln, attn=stage_attn, dwconv=stage_dwconv, vocoder=stage_vocoder,
+def stage_iso():
+    """Feed the oracle's intermediates into each GPU stage (isolates numerical drift from logic errors)."""
+    from seamless_communication_b200.models.unity import load_unity_model
+
+    cfg, vc, sd, vsd, toks = _tiny()
+    waves = S.make_waveforms(3, 32000)
+    uo = UnityOracle(cfg.to_dict(), sd, toks)
+    trace = {"sentence": 1}
+    ref = s2st(uo, VocoderOracle(vc.to_dict(), vsd), waves, "spa", 25, 45, hard_max=24, trace=trace)
+    model = load_unity_model("tiny_v2", state_dict=sd, tokenizers=toks)
+    eng = model.engine
+    M = cfg.model_dim
+    enc = Seq(3, ref["enc"].shape[1], M, buf=ref["enc"].to(dev).half().reshape(-1, M).contiguous())
+    ts = ref["text_seqs"].to(dev)
+    tl = torch.tensor([len(s) - 1 for s in ref["text_ids"]], dtype=torch.int32, device=dev)
+    dec = eng.decode_full(ts, tl, enc, None)
+    print("decode_full(oracle ids, oracle enc) rel err", rel(dec.buf.view(3, -1, M), ref["dec_out"]))
+    # teacher-forced logits of the oracle's best hypothesis vs oracle logits
+    lg = ops.gemm_raw(dec.buf, eng.w["text_embed"], cfg.text_vocab, out_f32=True).view(3, -1, cfg.text_vocab)
+    olg = uo.project(ref["dec_out"])
+    print("teacher-forced logits max abs err", (lg.float().cpu() - olg).abs().max().item(), "logit std", olg.std().item())
+    # beam search from the oracle's encoder output
+    hyps = eng.beam_search(enc, None, [cfg.text_eos, toks[0].lang_index("spa")], beam=5, hard_max=24)
+    for i in range(3):
+        same = hyps[i][0][1] == ref["text_ids"][i]
+        print(f"beam(oracle enc) sent {i}: equal {same} score {hyps[i][0][0]:.4f} vs {ref['hyps'][i][0][0]:.4f}; n_fin {len(hyps[i])} vs {len(ref['hyps'][i])}")
+        if not same:
+            # margin audit: score the GPU hypothesis with the oracle
+            ids = torch.tensor(hyps[i][0][1])[None]
+            h = uo.decoder(uo.embed_text(ids[:, :-1], 0), ref["enc"][i:i + 1], None)
+            lp = torch.log_softmax(uo.project(h).float(), -1)[0]
+            sc = sum(float(lp[t, ids[0, t + 1]]) for t in range(ids.shape[1] - 1)) / (ids.shape[1] - 1)
+            print(f"   oracle score of GPU hyp {sc:.4f} vs oracle best {ref['hyps'][i][0][0]:.4f}")
+            print("   gpu", hyps[i][0][1]); print("   ref", ref["text_ids"][i])
+    # T2U from the oracle's decoder output, free-running durations and oracle durations
+    dseq = Seq(3, ref["dec_out"].shape[1], M, lens=tl, buf=ref["dec_out"].to(dev).half().reshape(-1, M).contiguous())
+    units, ulens, aux = eng.t2u(dseq, ts)
+    print("t2u_enc rel err", rel(aux["t2u_enc"].buf.view(3, -1, M), ref["t2u_enc"]))
+    print("char_lens equal", torch.equal(aux["char_lens"].cpu().long(), ref["chars"][2]), "char_seq_lens", aux["char_seq_lens"].tolist(), ref["chars"][1].tolist())
+    cs = ref["chars"][0]
+    print("char_seqs equal", torch.equal(aux["char_seqs"].cpu().long()[:, :cs.shape[1]], cs))
+    nd = (aux["dur"].cpu().long() != ref["dur"]).sum().item()
+    print("durations differing", nd, "of", ref["dur"].numel(), "unit_lens", ulens.tolist(), ref["unit_lens"].tolist())
+    units2, ulens2, aux2 = eng.t2u(dseq, ts, durations=ref["dur"])
+    z = aux2["fft_out"]
+    print("fft_out (oracle durations) rel err", rel(z.data(), ref["fft_out"]))
+    for i in range(3):
+        n = int(ref["unit_lens"][i])
+        a, b = units2[i, :n].cpu(), ref["units"][i, :n]
+        print(f"units (oracle durations) sent {i}: differing {(a != b).sum().item()} of {n}")
+
+
+STAGES = dict(iso=stage_iso, gemm=stage_gemm, fbank=stage_fbank, ln=stage_ln, attn=stage_attn, dwconv=stage_dwconv, vocoder=stage_vocoder,
               e2e=stage_e2e)
 
 if __name__ == "__main__":
