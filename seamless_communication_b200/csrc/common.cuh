@@ -6,6 +6,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <utility>
+
 #include "../../include/seamless_b200.h"
 
 namespace sb {
@@ -43,6 +45,30 @@ inline void count_launch(int n = 1) { g_launch_count += n; }
     }                                                                                    \
     sb::count_launch();                                                                  \
   } while (0)
+
+// Programmatic dependent launch (PDL): every kernel of the path triggers its dependents at entry and waits for its
+// prerequisites right before it first touches data produced upstream, so launch latency, prologues (barrier init,
+// TMEM allocation, descriptor fetch) and - in the GEMM - the weight loads of kernel N+1 overlap with kernel N.
+// Both instructions are no-ops when the kernel was launched without the attribute.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -17,6 +17,8 @@ __global__ void embed_kernel(const int* __restrict__ ids, long long ids_ld, cons
                              const elem_t* __restrict__ embed, const float* __restrict__ pos, float scale,
                              elem_t* __restrict__ x, int dim) {
   // grid: (rows, L); x row = r*L + t.  With step_ptr the single column `*step_ptr` is embedded at position *step_ptr.
+  pdl_trigger();
+  pdl_wait();
   const int r = blockIdx.x, t = blockIdx.y;
   const int id_col0 = step_ptr ? *step_ptr : 0, pos0 = id_col0;
   const int tok = ids[(long long)r * ids_ld + id_col0 + t];
@@ -45,18 +47,18 @@ __device__ __forceinline__ void attend_one(const elem_t* __restrict__ qp, int nk
     for (int e = 0; e < 4; ++e) { float2 f = __half22float2(hh[e]); q[2 * e] = f.x; q[2 * e + 1] = f.y; }
   }
   float mx = -INFINITY;
-  // 16 keys per iteration: 4 independent 16-byte loads in flight per lane
-  for (int t0 = 0; t0 < nkeys; t0 += 16) {
-    uint4 u[4];
-    bool ok[4];
+  // 32 keys per iteration: 8 independent 16-byte loads in flight per lane
+  for (int t0 = 0; t0 < nkeys; t0 += 32) {
+    uint4 u[8];
+    bool ok[8];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 8; ++i) {
       const int t = t0 + 4 * i + kg;
       ok[i] = t < nkeys;
       u[i] = ok[i] ? *reinterpret_cast<const uint4*>(kptr(t) + dc * 8) : make_uint4(0, 0, 0, 0);
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 8; ++i) {
       const __half2* hh = reinterpret_cast<const __half2*>(&u[i]);
       float acc = 0.f;
 #pragma unroll
@@ -84,18 +86,18 @@ __device__ __forceinline__ void attend_one(const elem_t* __restrict__ qp, int nk
   float o[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) o[e] = 0.f;
-  for (int t0 = 0; t0 < nkeys; t0 += 16) {
-    uint4 u[4];
-    float pw[4];
+  for (int t0 = 0; t0 < nkeys; t0 += 32) {
+    uint4 u[8];
+    float pw[8];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 8; ++i) {
       const int t = t0 + 4 * i + kg;
       const bool ok = t < nkeys;
       pw[i] = ok ? sc[t] : 0.f;
       u[i] = ok ? *reinterpret_cast<const uint4*>(vptr(t) + dc * 8) : make_uint4(0, 0, 0, 0);
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 8; ++i) {
       const __half2* hh = reinterpret_cast<const __half2*>(&u[i]);
 #pragma unroll
       for (int e = 0; e < 4; ++e) { float2 f = __half22float2(hh[e]); o[2 * e] += pw[i] * f.x; o[2 * e + 1] += pw[i] * f.y; }
@@ -121,6 +123,8 @@ __global__ void __launch_bounds__(128) decode_self_attn_kernel(const elem_t* __r
                                                                int anc_ld, const int* __restrict__ step_ptr, int max_len,
                                                                elem_t* __restrict__ out, int rows, int heads) {
   extern __shared__ float sc_all[];  // [4][max_len] scores + [4][max_len] ancestor slots
+  pdl_trigger();
+  pdl_wait();
   const int step = *step_ptr;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r = blockIdx.x;
@@ -156,6 +160,8 @@ __global__ void __launch_bounds__(128) decode_cross_attn_kernel(const elem_t* __
                                                                 const int* __restrict__ enc_lens, int s_enc,
                                                                 elem_t* __restrict__ out, int rows, int beam, int heads) {
   extern __shared__ float sc_all[];  // [4][s_enc]
+  pdl_trigger();
+  pdl_wait();
   const int warp = threadIdx.x >> 5;
   const int r = blockIdx.x;
   const int h = blockIdx.y * 4 + warp;
@@ -191,6 +197,8 @@ __global__ void __launch_bounds__(TK_THREADS) logits_topk_kernel(const float* __
                                                                  int pad_idx, int eos_idx, int unk_idx, float unk_penalty, int K,
                                                                  float* __restrict__ cand_val, int* __restrict__ cand_idx,
                                                                  float* __restrict__ eos_lprob) {
+  pdl_trigger();
+  pdl_wait();
   const int r = blockIdx.x;
   const float* row = logits + (long long)r * ld;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -309,6 +317,8 @@ __global__ void __launch_bounds__(TK_THREADS) logits_topk_kernel(const float* __
 // ------------------------------------------------------------------------------------------- beam bookkeeping
 // one CTA per sentence; the step index is read from device memory so that one captured CUDA graph serves every step
 __global__ void __launch_bounds__(128) beam_step_kernel(const sb_beam_t p) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.x;
   const int beam = p.beam, K = p.K, ML = p.max_len;
   const int step = *p.step_ptr;
@@ -400,7 +410,11 @@ __global__ void __launch_bounds__(128) beam_step_kernel(const sb_beam_t p) {
   }
 }
 
-__global__ void step_advance_kernel(int* step_ptr) { *step_ptr += 1; }
+__global__ void step_advance_kernel(int* step_ptr) {
+  pdl_trigger();
+  pdl_wait();
+  *step_ptr += 1;
+}
 
 }  // namespace sb
 
@@ -408,9 +422,9 @@ extern "C" int sb_embed_step(const int32_t* seqs, int32_t seq_ld, const int32_t*
                              const void* pos_table, float scale, void* x, int32_t rows, int32_t dim, sb_stream_t stream) {
   using namespace sb;
   SB_REQUIRE(seqs && step_ptr && embed && pos_table && x && rows > 0 && dim % 2 == 0, SB_EINVAL, "sb_embed_step: bad args");
-  embed_kernel<<<dim3(rows, 1), 128, 0, (cudaStream_t)stream>>>(seqs, seq_ld, step_ptr, 1, (const elem_t*)embed,
-                                                                (const float*)pos_table, scale, (elem_t*)x, dim);
-  SB_LAUNCH_OK();
+  SB_CUDA_OK(launch_k(embed_kernel, dim3(rows, 1), dim3(128), 0, (cudaStream_t)stream, (const int*)seqs, (long long)seq_ld,
+                       (const int*)step_ptr, 1, (const elem_t*)embed, (const float*)pos_table, scale, (elem_t*)x, (int)dim));
+  count_launch();
   return SB_OK;
 }
 
@@ -432,9 +446,10 @@ extern "C" int sb_decode_self_attn(const void* qkv, void* kcache, void* vcache, 
              "sb_decode_self_attn: bad args");
   size_t smem = (size_t)8 * max_len * sizeof(float);
   SB_REQUIRE(smem <= 48 * 1024, SB_ENOSUP, "sb_decode_self_attn: max_len %d too large", max_len);
-  decode_self_attn_kernel<<<dim3(rows, (heads + 3) / 4), 128, smem, (cudaStream_t)stream>>>(
-      (const elem_t*)qkv, (elem_t*)kcache, (elem_t*)vcache, anc, anc_ld, step_ptr, max_len, (elem_t*)out, rows, heads);
-  SB_LAUNCH_OK();
+  SB_CUDA_OK(launch_k(decode_self_attn_kernel, dim3(rows, (heads + 3) / 4), dim3(128), smem, (cudaStream_t)stream,
+                       (const elem_t*)qkv, (elem_t*)kcache, (elem_t*)vcache, (const int*)anc, (int)anc_ld, (const int*)step_ptr,
+                       (int)max_len, (elem_t*)out, (int)rows, (int)heads));
+  count_launch();
   return SB_OK;
 }
 
@@ -444,9 +459,10 @@ extern "C" int sb_decode_cross_attn(const void* q, const void* k, const void* v,
   SB_REQUIRE(q && k && v && out && rows > 0 && heads > 0 && s_enc > 0 && beam > 0, SB_EINVAL, "sb_decode_cross_attn: bad args");
   size_t smem = (size_t)4 * s_enc * sizeof(float);
   SB_REQUIRE(smem <= 48 * 1024, SB_ENOSUP, "sb_decode_cross_attn: s_enc %d too large", s_enc);
-  decode_cross_attn_kernel<<<dim3(rows, (heads + 3) / 4), 128, smem, (cudaStream_t)stream>>>(
-      (const elem_t*)q, (const elem_t*)k, (const elem_t*)v, kv_ld, enc_lens, s_enc, (elem_t*)out, rows, beam, heads);
-  SB_LAUNCH_OK();
+  SB_CUDA_OK(launch_k(decode_cross_attn_kernel, dim3(rows, (heads + 3) / 4), dim3(128), smem, (cudaStream_t)stream,
+                       (const elem_t*)q, (const elem_t*)k, (const elem_t*)v, (long long)kv_ld, (const int*)enc_lens, (int)s_enc,
+                       (elem_t*)out, (int)rows, (int)beam, (int)heads));
+  count_launch();
   return SB_OK;
 }
 
@@ -456,9 +472,10 @@ extern "C" int sb_logits_topk(const float* logits, int64_t ld, int32_t rows, int
   using namespace sb;
   SB_REQUIRE(logits && cand_val && cand_idx && eos_lprob && rows > 0 && vocab > 0, SB_EINVAL, "sb_logits_topk: bad args");
   SB_REQUIRE(K > 0 && K <= TK_MAX, SB_ENOSUP, "sb_logits_topk: K=%d unsupported (<= %d)", K, TK_MAX);
-  logits_topk_kernel<<<rows, TK_THREADS, 0, (cudaStream_t)stream>>>(logits, ld, vocab, pad_idx, eos_idx, unk_idx, unk_penalty, K,
-                                                                    cand_val, cand_idx, eos_lprob);
-  SB_LAUNCH_OK();
+  SB_CUDA_OK(launch_k(logits_topk_kernel, dim3(rows), dim3(TK_THREADS), 0, (cudaStream_t)stream, logits, (long long)ld,
+                       (int)vocab, (int)pad_idx, (int)eos_idx, (int)unk_idx, unk_penalty, (int)K, cand_val, (int*)cand_idx,
+                       eos_lprob));
+  count_launch();
   return SB_OK;
 }
 
@@ -466,14 +483,14 @@ extern "C" int sb_beam_step(const sb_beam_t* p, sb_stream_t stream) {
   using namespace sb;
   SB_REQUIRE(p && p->batch > 0 && p->beam > 0 && p->beam <= 16 && p->K > 0, SB_EINVAL, "sb_beam_step: bad args");
   SB_REQUIRE(p->step_ptr != nullptr, SB_EINVAL, "sb_beam_step: step_ptr is null");
-  beam_step_kernel<<<p->batch, 128, 0, (cudaStream_t)stream>>>(*p);
-  SB_LAUNCH_OK();
+  SB_CUDA_OK(launch_k(beam_step_kernel, dim3(p->batch), dim3(128), 0, (cudaStream_t)stream, *p));
+  count_launch();
   return SB_OK;
 }
 
 extern "C" int sb_step_advance(int32_t* step_ptr, sb_stream_t stream) {
   SB_REQUIRE(step_ptr != nullptr, SB_EINVAL, "sb_step_advance: null");
-  sb::step_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_ptr);
-  SB_LAUNCH_OK();
+  SB_CUDA_OK(sb::launch_k(sb::step_advance_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, (int*)step_ptr));
+  sb::count_launch();
   return SB_OK;
 }

@@ -47,6 +47,8 @@ struct GemmArgs {
   int seq_rows, seq_halo, seq_len;
   const int* seq_lens;
   int tma_store;  // epilogue through smem + cp.async.bulk.tensor stores
+  int m_fast;  // skinny-M problems: blockIdx.x walks the M tiles so CTAs sharing a weight tile are co-scheduled (L2 reuse)
+  int kb_per_split;  // split-K: k-blocks per blockIdx.z slice (0 = no split); slice z writes rows [z*m, (z+1)*m) of out
 };
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
@@ -158,11 +160,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint32_t* tmem_ptr_smem = (uint32_t*)(tmem_full_bar + 1);
   float* bias_s = (float*)(smem + STAGES * Cfg::STAGE_BYTES + 256);
 
+  pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN;
-  const int m0 = blockIdx.y * BM;
+  const int n0 = (g.m_fast ? blockIdx.y : blockIdx.x) * BN;
+  const int m0 = (g.m_fast ? blockIdx.x : blockIdx.y) * BM;
   const int cblocks = (g.c_in + BK - 1) / BK;
-  const int kblocks = g.taps * cblocks;
+  const int kb_total = g.taps * cblocks;
+  const int kb_begin = g.kb_per_split > 0 ? blockIdx.z * g.kb_per_split : 0;
+  const int kb_stop = g.kb_per_split > 0 ? min(kb_total, kb_begin + g.kb_per_split) : kb_total;
+  const int kblocks = kb_stop - kb_begin;  // k-blocks of this CTA
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -195,12 +201,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int s = warp - 5;
       uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
       uint32_t ph = 0;
-      for (int kb = s; kb < kblocks; kb += STAGES, ph ^= 1) {
+      for (int kr = s; kr < kblocks; kr += STAGES, ph ^= 1) {
         mbar_wait(&empty_bar[s], ph ^ 1);
         mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+        const int kb = kb_begin + kr;
         const int tap = kb / cblocks, c0 = (kb - tap * cblocks) * BK;
-        tma_load_2d(sa, &tmA, &full_bar[s], c0, m0 + g.a_row0 + tap * g.dil);
+        // weights first: they do not depend on the upstream kernel, so under PDL they stream while it still runs
         tma_load_2d(sa + A_TILE_BYTES, &tmW, &full_bar[s], tap * g.c_in + c0, n0);
+        if (kr == s) pdl_wait();
+        tma_load_2d(sa, &tmA, &full_bar[s], c0, m0 + g.a_row0 + tap * g.dil);
       }
     }
   } else if (warp == 4) {
@@ -208,7 +217,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       // instruction descriptor: D=f32, A=B=f16 (0) / bf16 (1), K-major both, N>>3, M>>4
       const uint32_t idesc = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-      int s = 0, cb = 0;
+      int s = 0, cb = kb_begin % cblocks;
       uint32_t ph = 0;
       for (int kb = 0; kb < kblocks; ++kb) {
         mbar_wait(&full_bar[s], ph);
@@ -229,12 +238,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // ------------------------------------------------------------------ epilogue (warps 0..3)
+    pdl_wait();  // residual reads / output writes below must not overtake the upstream kernel
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     const int row = warp * 32 + lane;
     const long long m = (long long)m0 + row;
     const bool row_ok = m < g.m;
-    const long long q = m + g.out_row0;
+    const long long q = m + g.out_row0 + (g.kb_per_split > 0 ? (long long)blockIdx.z * g.m : 0);
     const bool valid = row_ok && seq_row_valid(q, g.seq_rows, g.seq_halo, g.seq_len, g.seq_lens);
     const int n_out_total = g.glu ? g.n / 2 : g.n;
     // NOTE: every access to v[] below uses compile-time indices (fully unrolled loops with predicates); a single
@@ -391,7 +401,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (threadIdx.x == 0) {
         const int n_tile_out = g.glu ? BN / 2 : BN;
         const int oc0 = g.glu ? (n0 >> 1) : n0;
-        const int q0 = (int)(m0 + g.out_row0);
+        const int q0 = (int)(m0 + g.out_row0 + (g.kb_per_split > 0 ? (long long)blockIdx.z * g.m : 0));
         const int gcols = g.out_f32 ? 32 : 64;
         for (int c = 0; c < n_tile_out; c += gcols)
           if (oc0 + c < n_out_total) tma_store_2d(&tmO, smem + (c / gcols) * 16384, oc0 + c, q0);
@@ -467,10 +477,12 @@ static void fill_args(const sb_gemm_t* g, GemmArgs* a) {
   a->out_row0 = g->out_row0;
   a->seq_rows = g->seq_rows; a->seq_halo = g->seq_halo; a->seq_len = g->seq_len; a->seq_lens = g->seq_lens;
   a->tma_store = 0;
+  a->kb_per_split = 0;
+  a->m_fast = 0;
 }
 
 template <int BN>
-static int launch(const sb_gemm_t* g, cudaStream_t st) {
+static int launch(const sb_gemm_t* g, cudaStream_t st, int splits = 1) {
   using Cfg = TileCfg<BN>;
   static bool configured = false;
   if (!configured) {
@@ -494,8 +506,19 @@ static int launch(const sb_gemm_t* g, cudaStream_t st) {
   static int force_direct = -1;
   if (force_direct < 0) { const char* e = getenv("SB_GEMM_DIRECT_STORE"); force_direct = e ? atoi(e) : 0; }
   if (force_direct) tma_ok = false;
+  int kb_per = 0;
+  if (splits > 1) {
+    const int kb_total = g->taps * ((g->c_in + BK - 1) / BK);
+    kb_per = (kb_total + splits - 1) / splits;
+    splits = (kb_total + kb_per - 1) / kb_per;
+    args.kb_per_split = kb_per;
+    // slice z stores only rows [z*m, z*m + m): clip each slice with its own row bound is impossible with one map,
+    // so the M tail of a slice must not spill into the next slice -> direct stores unless m is a multiple of 128
+    if (g->m % BM != 0) tma_ok = false;
+  }
   if (tma_ok) {
-    rc = make_tmap(&tmO, g->out, (uint64_t)n_out_total, (uint64_t)(g->out_row0 + g->m), (uint64_t)g->out_ld, BM, esize);
+    rc = make_tmap(&tmO, g->out, (uint64_t)n_out_total, (uint64_t)(g->out_row0 + (long long)g->m * (splits > 1 ? splits : 1)),
+                   (uint64_t)g->out_ld, BM, esize);
     if (rc) return rc;
     if (g->out2 != nullptr) {
       rc = make_tmap(&tmO2, g->out2, (uint64_t)n_out_total, (uint64_t)(g->out_row0 + g->m), (uint64_t)g->out2_ld, BM, 2);
@@ -508,9 +531,13 @@ static int launch(const sb_gemm_t* g, cudaStream_t st) {
     tmO = tmA;
     tmO2 = tmA;
   }
-  dim3 grid((g->n + BN - 1) / BN, (g->m + BM - 1) / BM);
-  gemm_tc_kernel<BN><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmW, tmO, tmO2, args);
-  SB_LAUNCH_OK();
+  dim3 grid((g->n + BN - 1) / BN, (g->m + BM - 1) / BM, splits > 1 ? splits : 1);
+  if (g->m <= 2 * BM && grid.y > 1) {
+    args.m_fast = 1;
+    grid = dim3(grid.y, grid.x, grid.z);
+  }
+  SB_CUDA_OK(launch_k(gemm_tc_kernel<BN>, grid, dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, tmA, tmW, tmO, tmO2, args));
+  count_launch();
   return SB_OK;
 }
 
@@ -570,6 +597,18 @@ extern "C" int sb_gemm(const sb_gemm_t* g, sb_stream_t stream) {
   if (g->n >= 64 && tiles(64) >= 148) return sb::launch<64>(g, st);
   if (g->n > 64) return sb::launch<64>(g, st);
   return sb::launch<32>(g, st);
+}
+
+// split-K: raw fp32 partial products, slice z at rows [z*m, (z+1)*m) of `partials` (ld = n); no epilogue math
+extern "C" int sb_gemm_splitk(const sb_gemm_t* g_in, int32_t splits, float* partials, sb_stream_t stream) {
+  int rc = sb::validate(g_in);
+  if (rc) return rc;
+  SB_REQUIRE(splits >= 1 && partials != nullptr && !g_in->glu, SB_EINVAL, "sb_gemm_splitk: bad args");
+  sb_gemm_t g = *g_in;
+  g.bias = nullptr; g.act = SB_ACT_NONE; g.alpha = 1.f; g.gamma = 1.f; g.res1 = nullptr; g.res2 = nullptr;
+  g.out = partials; g.out_ld = g.n; g.out_f32 = 1; g.out2 = nullptr; g.out_row0 = 0; g.seq_rows = 0;
+  if (g.n >= 128) return sb::launch<128>(&g, (cudaStream_t)stream, splits);
+  return sb::launch<64>(&g, (cudaStream_t)stream, splits);
 }
 
 extern "C" int sb_gemm_ref(const sb_gemm_t* g, sb_stream_t stream) {

@@ -1,5 +1,6 @@
 // Library-level state: error string, launch counter, small utility kernels.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -7,6 +8,11 @@
 namespace sb {
 static thread_local char g_err[512] = "";
 long long g_launch_count = 0;
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("SB_PDL"); v = (e != nullptr && atoi(e) != 0) ? 1 : 0;  // opt-in: measured slower than plain graph edges on B200 (profiles/r01_notes.md) }
+  return v != 0;
+}
 void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);

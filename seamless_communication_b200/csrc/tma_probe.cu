@@ -10,14 +10,22 @@ __device__ __forceinline__ bool p_try(uint64_t* bar, uint32_t parity) {
                : "=r"(ok) : "r"(p_smem_u32(bar)), "r"(parity) : "memory");
   return ok != 0;
 }
-__device__ __forceinline__ void p_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ bool p_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(p_smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ int g_wait_mode = 0;
+__device__ __forceinline__ void p_wait(uint64_t* bar, uint32_t parity, int mode = 0) {
   uint32_t spins = 0;
-  while (!p_try(bar, parity)) { if (++spins > (1u << 26)) __trap(); }
+  if (mode == 0) { while (!p_try(bar, parity)) { if (++spins > (1u << 26)) __trap(); } }
+  else { while (!p_test(bar, parity)) { if (++spins > (1u << 28)) __trap(); } }
 }
 
 // grid: ctas; block: 64 threads (warp 0 = issuers, warp 1 lane 0 = consumer)
 __global__ void __launch_bounds__(64) tma_probe_kernel(const __grid_constant__ CUtensorMap tm, int stages, int box_rows,
-                                                       int issuers, int iters, int rows_total, long long* cycles_out) {
+                                                       int issuers, int iters, int rows_total, long long* cycles_out, int mode) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int stage_bytes = box_rows * 128;
@@ -35,23 +43,24 @@ __global__ void __launch_bounds__(64) tma_probe_kernel(const __grid_constant__ C
   long long t0 = clock64();
   const int sub_rows = box_rows / issuers;  // each issuer loads a sub-box of sub_rows rows (tensor map box = sub_rows)
   if (warp == 0 && lane < issuers) {
+    int s = 0; uint32_t ph = 0;
+    int row = (int)((long long)blockIdx.x * 7919 * box_rows % (rows_total - 2 * box_rows)) + lane * sub_rows;
     for (int it = 0; it < iters; ++it) {
-      const int s = it % stages;
-      const uint32_t ph = (it / stages) & 1;
-      p_wait(&empty[s], ph ^ 1);
+      p_wait(&empty[s], ph ^ 1, mode);
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(p_smem_u32(&full[s])), "r"(sub_rows * 128) : "memory");
-      int row = (int)(((long long)blockIdx.x * iters + it) * box_rows % (rows_total - box_rows)) + lane * sub_rows;
       int col = (it & 7) * 64;
+      row += box_rows; if (row >= rows_total - 2 * box_rows) row -= rows_total - 2 * box_rows;
       asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                    ::"r"(p_smem_u32(smem + s * stage_bytes + lane * sub_rows * 128)), "l"(reinterpret_cast<uint64_t>(&tm)),
                      "r"(p_smem_u32(&full[s])), "r"(col), "r"(row) : "memory");
+      if (++s == stages) { s = 0; ph ^= 1; }
     }
   } else if (warp == 1 && lane == 0) {
+    int s = 0; uint32_t ph = 0;
     for (int it = 0; it < iters; ++it) {
-      const int s = it % stages;
-      const uint32_t ph = (it / stages) & 1;
-      p_wait(&full[s], ph);
+      p_wait(&full[s], ph, mode);
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(p_smem_u32(&empty[s])) : "memory");
+      if (++s == stages) { s = 0; ph ^= 1; }
     }
   }
   __syncthreads();
@@ -64,7 +73,7 @@ typedef CUresult (*EncFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, 
                           CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 extern "C" int sb_tma_probe(const void* base, int64_t rows_total, int64_t ld_elems, int ctas, int stages, int box_rows,
-                            int issuers, int iters, long long* cycles_out, sb_stream_t stream) {
+                            int issuers, int iters, long long* cycles_out, sb_stream_t stream, int mode) {
   void* p = nullptr;
   cudaDriverEntryPointQueryResult q;
   SB_CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
@@ -79,7 +88,7 @@ extern "C" int sb_tma_probe(const void* base, int64_t rows_total, int64_t ld_ele
   SB_REQUIRE(r == CUDA_SUCCESS, SB_ECUDA, "encode failed %d", (int)r);
   size_t smem = (size_t)stages * box_rows * 128 + 1024 + 256;
   SB_CUDA_OK(cudaFuncSetAttribute(sb::tma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  sb::tma_probe_kernel<<<ctas, 64, smem, (cudaStream_t)stream>>>(tm, stages, box_rows, issuers, iters, (int)rows_total, cycles_out);
+  sb::tma_probe_kernel<<<ctas, 64, smem, (cudaStream_t)stream>>>(tm, stages, box_rows, issuers, iters, (int)rows_total, cycles_out, mode);
   SB_LAUNCH_OK();
   return SB_OK;
 }

@@ -251,33 +251,39 @@ class UnitYEngine:
 
     def _decoder_step_forward(self, st):
         """One incremental decoder step for R rows; all shapes static, step index read from st['step'] on device.
-        The residual stream x is updated in place (the GEMM epilogue reads res1 and writes out element-wise)."""
+        The three residual GEMMs of a layer (self-attn out, cross-attn out, FFN out) run split-K so that all SMs stream
+        weights even at M = R rows, and their reduction (+bias, +residual) is fused into the LayerNorm that follows."""
         lib = _lib.load()
         c, M, H = self.cfg, self.M, self.H
         R, stream = st["R"], ops._stream()
-        x = st["x"]
-        check(lib.sb_embed_step(st["seqs"].data_ptr(), st["ML"], st["step"].data_ptr(), self.w["text_embed"].data_ptr(),
+        x, h, part = st["x"], st["h"], st["partials"]
+        w = self.w
+        check(lib.sb_embed_step(st["seqs"].data_ptr(), st["ML"], st["step"].data_ptr(), w["text_embed"].data_ptr(),
                                 self.pos.data_ptr(), math.sqrt(M), x.buf.data_ptr(), R, M, stream), "sb_embed_step")
+        self._ln(x, "text_decoder.layers.0.self_attn_layer_norm", out=h)
+        S_ATT, S_FFN = st["splits_attn"], st["splits_ffn"]
         for i in range(c.dec_layers):
             p = f"text_decoder.layers.{i}"
-            h = self._ln(x, p + ".self_attn_layer_norm", out=st["h"])
+            nxt = f"text_decoder.layers.{i + 1}.self_attn_layer_norm" if i + 1 < c.dec_layers else "text_decoder.layer_norm"
             qkv = self._lin(h, p + ".self_attn.qkv", 3 * M, out=st["qkv"])
             check(lib.sb_decode_self_attn(qkv.buf.data_ptr(), st["kc"][i].data_ptr(), st["vc"][i].data_ptr(),
                                           st["anc"].data_ptr(), st["ML"], st["step"].data_ptr(), st["ML"],
                                           st["att"].buf.data_ptr(), R, H, stream), "sb_decode_self_attn")
-            self._lin(st["att"], p + ".self_attn.output_proj", M, res1=x, out=x)
-            h = self._ln(x, p + ".encoder_decoder_attn_layer_norm", out=st["h"])
+            ops.gemm_splitk(st["att"], w[p + ".self_attn.output_proj.w"], M, S_ATT, part)
+            ops.splitk_reduce_ln(part, S_ATT, w[p + ".self_attn.output_proj.b"], x, w[p + ".encoder_decoder_attn_layer_norm.w"],
+                                 w[p + ".encoder_decoder_attn_layer_norm.b"], h)
             q = self._lin(h, p + ".encoder_decoder_attn.q_proj", M, out=st["q"])
             kv = st["cross_kv"][i].buf
             check(lib.sb_decode_cross_attn(q.buf.data_ptr(), kv.data_ptr(), kv[:, M:].data_ptr(), kv.stride(0),
                                            ops._p(st["enc_lens"]), st["S_enc"], st["att"].buf.data_ptr(), R, st["beam"], H,
                                            stream), "sb_decode_cross_attn")
-            self._lin(st["att"], p + ".encoder_decoder_attn.output_proj", M, res1=x, out=x)
-            h = self._ln(x, p + ".ffn_layer_norm", out=st["h"])
+            ops.gemm_splitk(st["att"], w[p + ".encoder_decoder_attn.output_proj.w"], M, S_ATT, part)
+            ops.splitk_reduce_ln(part, S_ATT, w[p + ".encoder_decoder_attn.output_proj.b"], x, w[p + ".ffn_layer_norm.w"],
+                                 w[p + ".ffn_layer_norm.b"], h)
             t = self._lin(h, p + ".ffn.inner_proj", c.dec_ffn_dim, act=ACT_RELU, out=st["ffn"])
-            self._lin(t, p + ".ffn.output_proj", M, res1=x, out=x)
-        h = self._ln(x, "text_decoder.layer_norm", out=st["h"])
-        ops.gemm(h, self.w["text_embed"], c.text_vocab, None, out=st["logits"], out_f32=True)
+            ops.gemm_splitk(t, w[p + ".ffn.output_proj.w"], M, S_FFN, part)
+            ops.splitk_reduce_ln(part, S_FFN, w[p + ".ffn.output_proj.b"], x, w[nxt + ".w"], w[nxt + ".b"], h)
+        ops.gemm(h, w["text_embed"], c.text_vocab, None, out=st["logits"], out_f32=True)
 
     def _decoder_step_select(self, st):
         lib = _lib.load()
@@ -313,6 +319,10 @@ class UnitYEngine:
         st["vc"] = [torch.empty((ML, R, M), dtype=F16, device=dev) for _ in range(c.dec_layers)]
         for name, width in (("x", M), ("h", M), ("q", M), ("att", M), ("qkv", 3 * M), ("ffn", c.dec_ffn_dim)):
             st[name] = Seq(1, R, width)
+        k_att, k_ffn = max(M // 64, 1), max(c.dec_ffn_dim // 64, 1)  # k-blocks of the two residual GEMM kinds
+        st["splits_attn"] = max(1, min(4, k_att // 4))
+        st["splits_ffn"] = max(1, min(8, k_ffn // 8))
+        st["partials"] = torch.empty((max(st["splits_attn"], st["splits_ffn"]) * R, M), dtype=torch.float32, device=dev)
         st["logits"] = Seq(1, R, c.text_vocab, dtype=torch.float32, buf=torch.empty(
             (R, (c.text_vocab + 7) // 8 * 8), dtype=torch.float32, device=dev))
         st["cand_val"] = torch.empty((R, K), dtype=torch.float32, device=dev)
