@@ -10,7 +10,8 @@ static thread_local char g_err[512] = "";
 long long g_launch_count = 0;
 bool pdl_enabled() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("SB_PDL"); v = (e != nullptr && atoi(e) != 0) ? 1 : 0;  // opt-in: measured slower than plain graph edges on B200 (profiles/r01_notes.md) }
+  // opt-in (SB_PDL=1): measured slower than plain graph edges on B200 in round 1 (profiles/r01_notes.md)
+  if (v < 0) { const char* e = getenv("SB_PDL"); v = (e != nullptr && atoi(e) != 0) ? 1 : 0; }
   return v != 0;
 }
 void set_error(const char* fmt, ...) {
