@@ -1,0 +1,151 @@
+"""CPU-side tests: C-ABI library loads and exports every declared symbol, host logic mirrors the reference's, the
+data-parallel plumbing works over gloo with world_size 2.  No kernel is launched here."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from seamless_communication_b200 import _lib, config as C, synthetic as S
+from seamless_communication_b200.inference.generator import SequenceGeneratorOptions, remove_consecutive_repeated_ngrams
+from seamless_communication_b200.inference.translator import Modality, Task, Translator
+from seamless_communication_b200.models.unity.unit_tokenizer import UnitTokenizer
+from seamless_communication_b200.nn import PaddingMask, get_seqs_and_padding_mask
+from seamless_communication_b200.parallel import shard_bounds
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = os.path.join(ROOT, "tests", "golden")
+
+
+def test_library_exports_every_header_symbol():
+    hdr = open(os.path.join(ROOT, "include", "seamless_b200.h")).read()
+    declared = set(re.findall(r"\b(sb_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"sb_stream_t", "sb_gemm_t", "sb_beam_t"}
+    lib = _lib.load()
+    missing = [n for n in sorted(declared) if not hasattr(lib, n)]
+    assert not missing, f"symbols declared in include/seamless_b200.h but not exported: {missing}"
+    assert set(_lib.PROTOTYPES) >= declared, sorted(declared - set(_lib.PROTOTYPES))
+    assert lib.sb_version() >= 1
+
+
+def test_no_cpu_fallback():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError):
+        Translator("seamlessM4T_v2_tiny", "vocoder_v2_tiny", device=torch.device("cpu"))
+    with pytest.raises(RuntimeError):
+        _lib.require_cuda()
+
+
+def test_unit_tokenizer_matches_reference_kats():
+    d = np.load(os.path.join(G, "unit_tokenizer.npz"))
+    langs = ["eng", "deu", "fra"]
+    for arch in ("nar_multilingual_v2", "base"):
+        tk = UnitTokenizer(100, langs, arch)
+        assert tk.vocab_info.size == int(d[arch + ".vocab_size"])
+        assert [tk.lang_to_index(l) for l in langs] == d[arch + ".lang_index"].tolist()
+        assert tk.index_to_lang(tk.lang_to_index("fra")) == "fra"
+        enc = tk.create_encoder("deu")
+        assert np.array_equal(enc(torch.from_numpy(d[arch + ".enc_in"])).numpy(), d[arch + ".enc_out"])
+        dec = tk.create_decoder()
+        assert np.array_equal(dec(torch.from_numpy(d[arch + ".dec_in"])).numpy(), d[arch + ".dec_out"])
+    with pytest.raises(ValueError):
+        UnitTokenizer(100, langs, "base").lang_to_index("xyz")
+    with pytest.raises(ValueError):
+        UnitTokenizer(100, langs, "base").create_encoder("xyz")
+    # vocabulary sizes of the reference's own unit test (tests/unit/models/unity/test_unity.py:24,41)
+    assert UnitTokenizer(100, langs, "base").vocab_info.size == 112
+    assert UnitTokenizer(100, langs, "nar_multilingual_v2").vocab_info.size == 108
+
+
+def test_ngram_filter_and_options_defaults():
+    assert remove_consecutive_repeated_ngrams([1, 2, 2, 3]) == [1, 2, 3]
+    assert remove_consecutive_repeated_ngrams([1, 2, 3, 1, 2, 3, 4]) == [1, 2, 3, 4]
+    assert remove_consecutive_repeated_ngrams([]) == []
+    o = SequenceGeneratorOptions()
+    assert (o.beam_size, o.soft_max_seq_len, o.hard_max_seq_len, o.unk_penalty, o.len_penalty) == (5, (1, 200), 1024, 0.0, 1.0)
+
+
+def test_task_routing_and_padding_mask():
+    assert Translator.get_modalities_from_task_str("s2st") == (Modality.SPEECH, Modality.SPEECH)
+    assert Translator.get_modalities_from_task_str("S2TT") == (Modality.SPEECH, Modality.TEXT)
+    assert Translator.get_modalities_from_task_str("asr") == (Modality.SPEECH, Modality.TEXT)
+    assert Translator.get_modalities_from_task_str("t2tt") == (Modality.TEXT, Modality.TEXT)
+    assert Translator.get_modalities_from_task_str("t2st") == (Modality.TEXT, Modality.SPEECH)
+    with pytest.raises(ValueError):
+        Translator.get_modalities_from_task_str("s2x")
+    assert [t.name for t in Task] == ["S2ST", "S2TT", "T2ST", "T2TT", "ASR"]
+    m = PaddingMask(torch.tensor([3, 1]), 4)
+    assert m.materialize().tolist() == [[True, True, True, False], [True, False, False, False]]
+    assert m.trim(1).seq_lens.tolist() == [2, 0] and m.trim(1).batch_seq_len == 3
+    seqs, mask = get_seqs_and_padding_mask({"seqs": torch.zeros(2, 4, 80), "seq_lens": torch.tensor([4, 2]), "is_ragged": True})
+    assert mask is not None and mask.seq_lens.tolist() == [4, 2]
+    assert get_seqs_and_padding_mask({"seqs": torch.zeros(2, 4), "seq_lens": torch.tensor([4, 4]), "is_ragged": False})[1] is None
+
+
+def test_synthetic_assets_follow_reference_layout():
+    cfg = C.tiny_v2()
+    tok, ctok = S.make_tokenizers(cfg)
+    assert tok.vocab_info.size == cfg.text_vocab and (tok.vocab_info.pad_idx, tok.vocab_info.unk_idx, tok.vocab_info.eos_idx) == (0, 1, 3)
+    enc = tok.create_encoder(task="translation", lang="spa", mode="target")
+    assert enc.prefix_indices.tolist() == [3, tok.lang_index("spa")]  # [</s>, __spa__] (ggml_convert.py:131-135)
+    src = tok.create_encoder(lang="eng", mode="source")
+    ids = src("aaab aaac").tolist()
+    assert ids[0] == tok.lang_index("eng") and ids[-1] == 3
+    assert tok.create_decoder()(torch.tensor(ids)) == "aaab aaac"
+    with pytest.raises(ValueError):
+        tok.create_encoder(lang="xxx")
+    sd = S.make_unity_state_dict(cfg, 0)
+    # names a maintainer would recognise from convert_unity_checkpoint (models/unity/loader.py:206-386)
+    for k in ("speech_encoder.inner.layers.0.self_attn.sdpa.rel_k_embed.weight", "speech_encoder.adaptor_layers.0.residual_conv.weight",
+              "text_decoder.layers.1.encoder_decoder_attn.q_proj.weight", "t2u_model.decoder.layers.0.conv1d.conv1.weight",
+              "t2u_model.decoder_frontend.variance_adaptor.duration_predictor.conv1.0.weight", "final_proj.weight"):
+        assert k in sd
+    assert sd["final_proj.weight"] is sd["text_decoder_frontend.embed.weight"]  # TiedProjection (builder.py:451)
+    assert sd["speech_encoder.inner.layers.0.conv.depthwise_conv.weight"].shape == (cfg.model_dim, 1, 31)
+    full = C.base_v2()
+    assert (full.model_dim, full.enc_layers, full.dec_layers, full.text_vocab, full.unit_vocab, full.char_vocab) == \
+           (1024, 24, 24, 256102, 10082, 10943)
+
+
+def test_shard_bounds_cover_batch():
+    for n, w in ((256, 8), (33, 4), (3, 8)):
+        spans = [shard_bounds(n, w, r) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+
+
+_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from seamless_communication_b200.parallel import scatter_batch, gather_padded, shard_bounds
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:" + sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+rank = dist.get_rank()
+g = torch.arange(6 * 5, dtype=torch.float32).view(6, 5) if rank == 0 else None
+mine = scatter_batch(g, 3, (5,), torch.float32, "cpu")
+lo, hi = shard_bounds(6, 2, rank)
+assert torch.equal(mine, torch.arange(6 * 5, dtype=torch.float32).view(6, 5)[lo:hi]), mine
+# ranks produce different output lengths (rank r: 4 + r samples per row)
+out = mine[:, :1].repeat(1, 4 + rank) + rank
+outs, lens = gather_padded(out, torch.full((3,), 4 + rank, dtype=torch.int64))
+if rank == 0:
+    assert [o.shape for o in outs] == [torch.Size([3, 4]), torch.Size([3, 5])], [o.shape for o in outs]
+    assert torch.equal(outs[1][:, 0], torch.arange(6 * 5, dtype=torch.float32).view(6, 5)[3:, 0] + 1)
+    assert lens[1].tolist() == [5, 5, 5]
+dist.barrier()
+dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_scatter_gather_world_size_2_gloo(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(_WORKER)
+    port = str(29500 + (os.getpid() % 2000))
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                              text=True) for r in range(2)]
+    outs = [p.communicate(timeout=120)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
