@@ -163,6 +163,7 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--stages", action="store_true", help="also report per-stage GPU time")
+    ap.add_argument("--profile-only", action="store_true", help="one device-resident step only (for ncu launch lists)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -249,6 +250,11 @@ def main():
             ms = float(t.item())
         return ms / steps, launches
 
+    if args.profile_only:
+        step_device()
+        torch.cuda.synchronize()
+        print(json.dumps({"profile_only": True, "launches": ops.launch_count() + tr.model.engine.graph_kernels}))
+        return
     sampler = ClockSampler(local) if rank == 0 else None
     ms_dev, launches = timed(step_device, args.steps, args.warmup)
     clocks = sampler.stop() if sampler else None
