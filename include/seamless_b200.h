@@ -79,12 +79,14 @@ typedef struct {
 int sb_gemm(const sb_gemm_t* g, sb_stream_t stream);
 /* split-K variant for skinny-M / large-K products (the decoder's residual GEMMs at M = batch*beam rows): the K range is
  * cut into `splits` slices computed by different CTAs so every SM streams weights; slice z writes its raw fp32 partial
- * products to rows [z*m, (z+1)*m) of `partials` (row stride n).  Only a/w/shape fields of `g` are used. */
-int sb_gemm_splitk(const sb_gemm_t* g, int32_t splits, float* partials, sb_stream_t stream);
+ * products to rows [z*slice_rows, z*slice_rows + m) of `partials` (row stride n; slice_rows a multiple of 128 enables
+ * the TMA-store epilogue).  Only a/w/shape fields of `g` are used. */
+int sb_gemm_splitk(const sb_gemm_t* g, int32_t splits, float* partials, int64_t slice_rows, sb_stream_t stream);
 /* consumer of the partials: x += bias + sum_z partial[z] (x fp16 [rows][dim], updated in place) and h = LayerNorm(x).
  * Fuses the reduction into the LayerNorm that follows every residual GEMM of a pre-LN decoder layer
  * (StandardTransformerDecoderLayer, fairseq2.cpp:979-1060). */
-int sb_splitk_reduce_ln(const float* partials, int32_t splits, int32_t rows, int32_t dim, const float* bias, void* x,
+int sb_splitk_reduce_ln(const float* partials, int32_t splits, int32_t rows, int64_t slice_rows, int32_t dim,
+                        const float* bias, void* x,
                         const float* ln_w, const float* ln_b, void* h, sb_stream_t stream);
 /* same contract on CUDA cores (fp32 accumulate); a debugging cross-check, never used by the product path */
 int sb_gemm_ref(const sb_gemm_t* g, sb_stream_t stream);

@@ -44,8 +44,8 @@ PROTOTYPES = {
     "sb_launch_count": [],
     "sb_gemm": [C.POINTER(GemmDesc), c_p],
     "sb_gemm_ref": [C.POINTER(GemmDesc), c_p],
-    "sb_gemm_splitk": [C.POINTER(GemmDesc), i32, c_p, c_p],
-    "sb_splitk_reduce_ln": [c_p, i32, i32, i32, c_p, c_p, c_p, c_p, c_p, c_p],
+    "sb_gemm_splitk": [C.POINTER(GemmDesc), i32, c_p, i64, c_p],
+    "sb_splitk_reduce_ln": [c_p, i32, i32, i64, i32, c_p, c_p, c_p, c_p, c_p, c_p],
     "sb_fbank": [c_p, i64, c_p, i32, c_p, i32, c_p, c_p, i32, c_p],
     "sb_layernorm": [c_p, c_p, c_p, c_p, c_p, c_p, i32, i32, i32, i32, i32, i32, i32, c_p, i32, c_p],
     "sb_attention": [c_p, i64, c_p, i64, c_p, i64, c_p, i64, i32, i32, i32, i32, i32, i32, i32, i32, c_p, i32, c_p, i32,

@@ -48,7 +48,8 @@ struct GemmArgs {
   const int* seq_lens;
   int tma_store;  // epilogue through smem + cp.async.bulk.tensor stores
   int m_fast;  // skinny-M problems: blockIdx.x walks the M tiles so CTAs sharing a weight tile are co-scheduled (L2 reuse)
-  int kb_per_split;  // split-K: k-blocks per blockIdx.z slice (0 = no split); slice z writes rows [z*m, (z+1)*m) of out
+  int kb_per_split;  // split-K: k-blocks per blockIdx.z slice (0 = no split)
+  long long slice_rows;  // split-K: slice z writes rows [z*slice_rows, z*slice_rows + m) of out
 };
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
@@ -86,6 +87,15 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
+}
+// One lane of a CONVERGED warp.  tcgen05.mma / tcgen05.commit / cp.async.bulk.tensor execute on the uniform datapath;
+// issued from an `if (lane == 0)` region the compiler must wrap each of them in an ELECT / BRA.U.ANY serialisation
+// loop (~150 cycles per instruction, measured with the per-k-block timeline in tools/gemm_timeline.py), whereas
+// under elect.sync it knows a single lane is active and emits the instruction directly.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -126,12 +136,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "memory");
 }
 
-template <int BN>
+template <int BN, bool DEEP = false>
 struct TileCfg {
-  static constexpr int STAGES = (BN >= 128) ? 3 : 4;
+  // DEEP: one CTA per SM with as many stages as fit - for skinny problems (few CTAs) whose K loop is a chain of
+  // ~1.4 us load round trips (tools/gemm_timeline.py); the default keeps 2 CTAs/SM so epilogues overlap main loops
+  static constexpr int STAGES = DEEP ? (BN >= 128 ? 6 : 8) : ((BN >= 128) ? 3 : 4);
   static constexpr int B_TILE_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
-  static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  // Accumulating tcgen05.mma instructions that target the same TMEM tile issue ~180 cycles apart (measured:
+  // 0.38 us per 64-deep k-block = 4 dependent MMAs, independent of N, tools/gemm_timeline.py), while a 128xBNx16 MMA
+  // keeps the tensor pipe busy for only BN/2 cycles.  The K loop therefore round-robins NACC independent accumulators
+  // (summed in the epilogue) so that several MMA chains are in flight.
+  static constexpr int NACC = BN >= 128 ? 2 : 4;
+  static constexpr int TMEM_COLS = NACC * BN < 32 ? 32 : NACC * BN;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + BN * 4;
   static constexpr int THREADS = 32 * (5 + STAGES);
   // epilogue staging reuses the (drained) pipeline stages: out groups first, out2 groups after them
@@ -146,11 +163,15 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, const void* 
                : "memory");
 }
 
-template <int BN>
-__global__ void __launch_bounds__(TileCfg<BN>::THREADS, 2)
+__device__ unsigned long long* g_timeline = nullptr;
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define TL(i) do { if (g_timeline != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) g_timeline[i] = gtime(); } while (0)
+
+template <int BN, bool DEEP>
+__global__ void __launch_bounds__(TileCfg<BN, DEEP>::THREADS, DEEP ? 1 : 2)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmO2, const GemmArgs g) {
-  using Cfg = TileCfg<BN>;
+  using Cfg = TileCfg<BN, DEEP>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -161,6 +182,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   float* bias_s = (float*)(smem + STAGES * Cfg::STAGE_BYTES + 256);
 
   pdl_trigger();
+  if (threadIdx.x == 0) TL(0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = (g.m_fast ? blockIdx.y : blockIdx.x) * BN;
   const int m0 = (g.m_fast ? blockIdx.x : blockIdx.y) * BM;
@@ -194,31 +216,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  if (threadIdx.x == 0) TL(1);
 
   if (warp >= 5) {
     // ------------------------------------------------------------------ TMA producers: warp 5+s owns stage s
-    if (lane == 0) {
+    {
       const int s = warp - 5;
       uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
       uint32_t ph = 0;
       for (int kr = s; kr < kblocks; kr += STAGES, ph ^= 1) {
         mbar_wait(&empty_bar[s], ph ^ 1);
-        mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
         const int kb = kb_begin + kr;
         const int tap = kb / cblocks, c0 = (kb - tap * cblocks) * BK;
-        // weights first: they do not depend on the upstream kernel, so under PDL they stream while it still runs
-        tma_load_2d(sa + A_TILE_BYTES, &tmW, &full_bar[s], tap * g.c_in + c0, n0);
-        if (kr == s) pdl_wait();
-        tma_load_2d(sa, &tmA, &full_bar[s], c0, m0 + g.a_row0 + tap * g.dil);
+        if (elect_one()) {
+          mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+          // weights first: they do not depend on the upstream kernel, so under PDL they stream while it still runs
+          tma_load_2d(sa + A_TILE_BYTES, &tmW, &full_bar[s], tap * g.c_in + c0, n0);
+          if (kr == s) pdl_wait();
+          tma_load_2d(sa, &tmA, &full_bar[s], c0, m0 + g.a_row0 + tap * g.dil);
+        }
+        __syncwarp();
       }
     }
   } else if (warp == 4) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (whole warp converged, one lane issues)
+    {
       // instruction descriptor: D=f32, A=B=f16 (0) / bf16 (1), K-major both, N>>3, M>>4
       const uint32_t idesc = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       int s = 0, cb = kb_begin % cblocks;
       uint32_t ph = 0;
+      uint32_t kstep = 0;  // running k-step index: accumulator kstep % NACC, first touch of each accumulator overwrites
       for (int kb = 0; kb < kblocks; ++kb) {
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
@@ -227,39 +254,65 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int ksteps = (g.c_in - cb * BK + 15) >> 4;
         if (ksteps > BK / 16) ksteps = BK / 16;
         if (++cb == cblocks) cb = 0;
-        for (int k = 0; k < ksteps; ++k) {
-          // advance 16 elements (32 B) along K inside the swizzle atom: +2 in the (addr >> 4) field
-          tc_mma_f16(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+        if (elect_one()) {
+          if (kb == 0) TL(2);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            if (k < ksteps) {
+              // advance 16 elements (32 B) along K inside the swizzle atom: +2 in the (addr >> 4) field
+              tc_mma_f16(tmem_base + ((kstep + k) % Cfg::NACC) * BN, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
+                         (kstep + k) >= (uint32_t)Cfg::NACC);
+            }
+          }
+          tc_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
+          if (kb == kblocks - 1) {
+            tc_commit(tmem_full_bar);  // accumulators complete
+            TL(3);
+          }
         }
-        tc_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
+        __syncwarp();
+        kstep += ksteps;
         if (++s == STAGES) { s = 0; ph ^= 1; }
       }
-      tc_commit(tmem_full_bar);    // accumulator complete
     }
   } else {
     // ------------------------------------------------------------------ epilogue (warps 0..3)
     pdl_wait();  // residual reads / output writes below must not overtake the upstream kernel
     mbar_wait(tmem_full_bar, 0);
+    if (threadIdx.x == 0) TL(4);
     tc_fence_after();
     const int row = warp * 32 + lane;
     const long long m = (long long)m0 + row;
     const bool row_ok = m < g.m;
-    const long long q = m + g.out_row0 + (g.kb_per_split > 0 ? (long long)blockIdx.z * g.m : 0);
+    const long long q = m + g.out_row0 + (g.kb_per_split > 0 ? (long long)blockIdx.z * g.slice_rows : 0);
     const bool valid = row_ok && seq_row_valid(q, g.seq_rows, g.seq_halo, g.seq_len, g.seq_lens);
     const int n_out_total = g.glu ? g.n / 2 : g.n;
     // NOTE: every access to v[] below uses compile-time indices (fully unrolled loops with predicates); a single
     // runtime-indexed access would push the whole array to local memory (seen in profiles/r01_gemm_v1_*.txt).
+    // accumulators that received at least one MMA: min(NACC, #k-steps of this CTA); the last channel block of a tap
+    // may hold fewer than 4 k-steps when c_in is not a multiple of 64
+    const int tail_steps = (g.c_in - (cblocks - 1) * BK + 15) >> 4;
+    const int n_tail = kb_stop / cblocks - kb_begin / cblocks;
+    const int total_steps = (BK / 16) * (kblocks - n_tail) + tail_steps * n_tail;
+    const int n_acc = total_steps < Cfg::NACC ? total_steps : Cfg::NACC;
     const bool has_res = valid && (g.res1 != nullptr || g.res2 != nullptr);
     const float post_scale = has_res ? g.gamma : g.alpha * g.gamma;
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       if (n0 + c0 >= g.n) break;  // warp-uniform
-      uint32_t r[32];
-      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
-      if (!row_ok) continue;
       float v[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + bias_s[c0 + j];
+      for (int j = 0; j < 32; ++j) v[j] = bias_s[c0 + j];
+#pragma unroll
+      for (int a = 0; a < Cfg::NACC; ++a) {
+        if (a < n_acc) {  // warp-uniform
+          uint32_t r[32];
+          tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * BN + c0), r);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(r[j]);
+        }
+      }
+      if (!row_ok) continue;
       int nv = 32;         // number of output values in this chunk
       int oc = n0 + c0;    // first output column
       if (g.glu) {
@@ -401,7 +454,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (threadIdx.x == 0) {
         const int n_tile_out = g.glu ? BN / 2 : BN;
         const int oc0 = g.glu ? (n0 >> 1) : n0;
-        const int q0 = (int)(m0 + g.out_row0 + (g.kb_per_split > 0 ? (long long)blockIdx.z * g.m : 0));
+        const int q0 = (int)(m0 + g.out_row0 + (g.kb_per_split > 0 ? (long long)blockIdx.z * g.slice_rows : 0));
         const int gcols = g.out_f32 ? 32 : 64;
         for (int c = 0; c < n_tile_out; c += gcols)
           if (oc0 + c < n_out_total) tma_store_2d(&tmO, smem + (c / gcols) * 16384, oc0 + c, q0);
@@ -413,8 +466,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   }
+  if (threadIdx.x == 0) TL(5);
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) TL(6);
   if (warp == 4) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS)
@@ -478,15 +533,16 @@ static void fill_args(const sb_gemm_t* g, GemmArgs* a) {
   a->seq_rows = g->seq_rows; a->seq_halo = g->seq_halo; a->seq_len = g->seq_len; a->seq_lens = g->seq_lens;
   a->tma_store = 0;
   a->kb_per_split = 0;
+  a->slice_rows = 0;
   a->m_fast = 0;
 }
 
-template <int BN>
-static int launch(const sb_gemm_t* g, cudaStream_t st, int splits = 1) {
-  using Cfg = TileCfg<BN>;
+template <int BN, bool DEEP = false>
+static int launch(const sb_gemm_t* g, cudaStream_t st, int splits = 1, long long slice_rows = 0) {
+  using Cfg = TileCfg<BN, DEEP>;
   static bool configured = false;
   if (!configured) {
-    SB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    SB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, DEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;
   }
   CUtensorMap tmA, tmW, tmO, tmO2;
@@ -512,12 +568,13 @@ static int launch(const sb_gemm_t* g, cudaStream_t st, int splits = 1) {
     kb_per = (kb_total + splits - 1) / splits;
     splits = (kb_total + kb_per - 1) / kb_per;
     args.kb_per_split = kb_per;
-    // slice z stores only rows [z*m, z*m + m): clip each slice with its own row bound is impossible with one map,
-    // so the M tail of a slice must not spill into the next slice -> direct stores unless m is a multiple of 128
-    if (g->m % BM != 0) tma_ok = false;
+    args.slice_rows = slice_rows > 0 ? slice_rows : g->m;
+    // one tensor map covers all slices, so an M-tail tile of slice z would spill into slice z+1 unless the slice
+    // stride is a multiple of the tile height
+    if (args.slice_rows % BM != 0) tma_ok = false;
   }
   if (tma_ok) {
-    rc = make_tmap(&tmO, g->out, (uint64_t)n_out_total, (uint64_t)(g->out_row0 + (long long)g->m * (splits > 1 ? splits : 1)),
+    rc = make_tmap(&tmO, g->out, (uint64_t)n_out_total, (uint64_t)(g->out_row0 + (splits > 1 ? args.slice_rows * splits : (long long)g->m)),
                    (uint64_t)g->out_ld, BM, esize);
     if (rc) return rc;
     if (g->out2 != nullptr) {
@@ -536,7 +593,7 @@ static int launch(const sb_gemm_t* g, cudaStream_t st, int splits = 1) {
     args.m_fast = 1;
     grid = dim3(grid.y, grid.x, grid.z);
   }
-  SB_CUDA_OK(launch_k(gemm_tc_kernel<BN>, grid, dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, tmA, tmW, tmO, tmO2, args));
+  SB_CUDA_OK(launch_k(gemm_tc_kernel<BN, DEEP>, grid, dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, tmA, tmW, tmO, tmO2, args));
   count_launch();
   return SB_OK;
 }
@@ -599,16 +656,22 @@ extern "C" int sb_gemm(const sb_gemm_t* g, sb_stream_t stream) {
   return sb::launch<32>(g, st);
 }
 
-// split-K: raw fp32 partial products, slice z at rows [z*m, (z+1)*m) of `partials` (ld = n); no epilogue math
-extern "C" int sb_gemm_splitk(const sb_gemm_t* g_in, int32_t splits, float* partials, sb_stream_t stream) {
+// split-K: raw fp32 partial products, slice z at rows [z*slice_rows, z*slice_rows + m) of `partials` (ld = n)
+extern "C" int sb_gemm_splitk(const sb_gemm_t* g_in, int32_t splits, float* partials, int64_t slice_rows, sb_stream_t stream) {
   int rc = sb::validate(g_in);
   if (rc) return rc;
   SB_REQUIRE(splits >= 1 && partials != nullptr && !g_in->glu, SB_EINVAL, "sb_gemm_splitk: bad args");
   sb_gemm_t g = *g_in;
   g.bias = nullptr; g.act = SB_ACT_NONE; g.alpha = 1.f; g.gamma = 1.f; g.res1 = nullptr; g.res2 = nullptr;
   g.out = partials; g.out_ld = g.n; g.out_f32 = 1; g.out2 = nullptr; g.out_row0 = 0; g.seq_rows = 0;
-  if (g.n >= 128) return sb::launch<128>(&g, (cudaStream_t)stream, splits);
-  return sb::launch<64>(&g, (cudaStream_t)stream, splits);
+  SB_REQUIRE(slice_rows >= g.m, SB_EINVAL, "sb_gemm_splitk: slice_rows (%lld) < m (%d)", (long long)slice_rows, g.m);
+  if (g.n >= 128) return sb::launch<128>(&g, (cudaStream_t)stream, splits, slice_rows);
+  return sb::launch<64>(&g, (cudaStream_t)stream, splits, slice_rows);
+}
+
+extern "C" int sb_gemm_debug_timeline(unsigned long long* buf) {
+  SB_CUDA_OK(cudaMemcpyToSymbol(sb::g_timeline, &buf, sizeof(buf)));
+  return SB_OK;
 }
 
 extern "C" int sb_gemm_ref(const sb_gemm_t* g, sb_stream_t stream) {

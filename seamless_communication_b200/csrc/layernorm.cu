@@ -101,6 +101,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const elem_t* __restrict
 // x_new = x + bias + sum_z partial[z]  (fp32 sum, rounded to fp16 like the unfused residual stream), h = LN(x_new).
 // One warp per row; dim <= 2048.  Consumer of sb_gemm_splitk for the decoder's residual GEMMs.
 __global__ void __launch_bounds__(256) splitk_reduce_ln_kernel(const float* __restrict__ partials, int splits, long long rows,
+                                                               long long slice_rows,
                                                                int dim, const float* __restrict__ bias, elem_t* __restrict__ x,
                                                                const float* __restrict__ w, const float* __restrict__ bvec,
                                                                elem_t* __restrict__ h) {
@@ -134,7 +135,7 @@ __global__ void __launch_bounds__(256) splitk_reduce_ln_kernel(const float* __re
         float4 p0[4], p1[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const float* pp = partials + ((long long)(z + u) * rows + row) * dim + off;
+          const float* pp = partials + ((long long)(z + u) * slice_rows + row) * dim + off;
           p0[u] = *reinterpret_cast<const float4*>(pp);
           p1[u] = *reinterpret_cast<const float4*>(pp + 4);
         }
@@ -145,7 +146,7 @@ __global__ void __launch_bounds__(256) splitk_reduce_ln_kernel(const float* __re
         }
       }
       for (; z < splits; ++z) {
-        const float* pp = partials + ((long long)z * rows + row) * dim + off;
+        const float* pp = partials + ((long long)z * slice_rows + row) * dim + off;
         const float4 p0 = *reinterpret_cast<const float4*>(pp), p1 = *reinterpret_cast<const float4*>(pp + 4);
         acc[0] += p0.x; acc[1] += p0.y; acc[2] += p0.z; acc[3] += p0.w; acc[4] += p1.x; acc[5] += p1.y; acc[6] += p1.z; acc[7] += p1.w;
       }
@@ -197,14 +198,15 @@ __global__ void __launch_bounds__(256) splitk_reduce_ln_kernel(const float* __re
 
 }  // namespace sb
 
-extern "C" int sb_splitk_reduce_ln(const float* partials, int32_t splits, int32_t rows, int32_t dim, const float* bias, void* x,
+extern "C" int sb_splitk_reduce_ln(const float* partials, int32_t splits, int32_t rows, int64_t slice_rows, int32_t dim,
+                                   const float* bias, void* x,
                                    const float* ln_w, const float* ln_b, void* h, sb_stream_t stream) {
   using namespace sb;
   SB_REQUIRE(partials && x && ln_w && ln_b && h && splits >= 1 && rows > 0, SB_EINVAL, "sb_splitk_reduce_ln: bad args");
   SB_REQUIRE(dim % 8 == 0 && dim <= 256 * LN_MAX_CHUNKS, SB_ENOSUP, "sb_splitk_reduce_ln: dim %d unsupported", dim);
   const int wpb = 1;
   SB_CUDA_OK(launch_k(splitk_reduce_ln_kernel, dim3((rows + wpb - 1) / wpb), dim3(wpb * 32), 0, (cudaStream_t)stream, partials,
-                       (int)splits, (long long)rows, (int)dim, bias, (elem_t*)x, ln_w, ln_b, (elem_t*)h));
+                       (int)splits, (long long)rows, (long long)slice_rows, (int)dim, bias, (elem_t*)x, ln_w, ln_b, (elem_t*)h));
   count_launch();
   return SB_OK;
 }

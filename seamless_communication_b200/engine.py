@@ -322,7 +322,8 @@ class UnitYEngine:
         k_att, k_ffn = max(M // 64, 1), max(c.dec_ffn_dim // 64, 1)  # k-blocks of the two residual GEMM kinds
         st["splits_attn"] = max(1, min(4, k_att // 4))
         st["splits_ffn"] = max(1, min(8, k_ffn // 8))
-        st["partials"] = torch.empty((max(st["splits_attn"], st["splits_ffn"]) * R, M), dtype=torch.float32, device=dev)
+        st["partials"] = torch.empty((max(st["splits_attn"], st["splits_ffn"]) * ops.slice_rows(R), M), dtype=torch.float32,
+                                     device=dev)
         st["logits"] = Seq(1, R, c.text_vocab, dtype=torch.float32, buf=torch.empty(
             (R, (c.text_vocab + 7) // 8 * 8), dtype=torch.float32, device=dev))
         st["cand_val"] = torch.empty((R, K), dtype=torch.float32, device=dev)

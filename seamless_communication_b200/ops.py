@@ -108,20 +108,25 @@ def gemm_raw(a: torch.Tensor, w: torch.Tensor, n: int, bias=None, *, act=ACT_NON
     return out
 
 
+def slice_rows(rows: int) -> int:
+    """Row stride between split-K slices: padded to the GEMM tile height so the TMA-store epilogue applies."""
+    return (rows + 127) // 128 * 128
+
+
 def gemm_splitk(a: Seq, w: torch.Tensor, n: int, splits: int, partials: torch.Tensor) -> None:
-    """Raw fp32 partial products of a (dense) Seq against w into partials[(z*rows + r), n] (see sb_gemm_splitk)."""
+    """Raw fp32 partial products of a (dense) Seq against w into partials[(z*slice_rows(rows) + r), n]."""
     lib = _lib.load()
     assert a.PH == 0 and a.Tp == a.T
     d = GemmDesc()
     d.a, d.a_rows, d.a_ld, d.c_in, d.taps, d.dil, d.a_row0 = a.buf.data_ptr(), a.B * a.T, a.buf.stride(0), a.C, 1, 1, 0
     d.w, d.n, d.m = w.data_ptr(), n, a.B * a.T
     d.out = partials.data_ptr()  # validated as non-null; sb_gemm_splitk overrides the epilogue fields
-    check(lib.sb_gemm_splitk(C.byref(d), splits, partials.data_ptr(), _stream()), "sb_gemm_splitk")
+    check(lib.sb_gemm_splitk(C.byref(d), splits, partials.data_ptr(), slice_rows(a.B * a.T), _stream()), "sb_gemm_splitk")
 
 
 def splitk_reduce_ln(partials: torch.Tensor, splits: int, bias, x: Seq, ln_w, ln_b, h: Seq) -> None:
     lib = _lib.load()
-    check(lib.sb_splitk_reduce_ln(partials.data_ptr(), splits, x.B * x.T, x.C, _p(bias), x.buf.data_ptr(), ln_w.data_ptr(),
+    check(lib.sb_splitk_reduce_ln(partials.data_ptr(), splits, x.B * x.T, slice_rows(x.B * x.T), x.C, _p(bias), x.buf.data_ptr(), ln_w.data_ptr(),
                                   ln_b.data_ptr(), h.buf.data_ptr(), _stream()), "sb_splitk_reduce_ln")
 
 

@@ -108,7 +108,7 @@ def test_gemm_glu_and_splitk(ops):
     want_x = (xk.buf.float() @ wk.float().t() + bk + resid.buf.float()).half()
     want_h = F.layer_norm(want_x.float(), (1024,), lw, lb, 1e-5)
     for splits in (1, 4, 8):
-        part = torch.empty((splits * 160, 1024), dtype=torch.float32, device=dev)
+        part = torch.empty((splits * ops.slice_rows(160), 1024), dtype=torch.float32, device=dev)
         xs = Seq(1, 160, 1024, buf=resid.buf.clone())
         h = Seq(1, 160, 1024)
         ops.gemm_splitk(xk, wk, 1024, splits, part)
