@@ -219,6 +219,16 @@ int sb_vocoder_embed(const int32_t* units, int32_t U, int32_t batch, const void*
 int sb_conv_post_tanh(const void* x, int32_t x_rows, int32_t x_halo, int32_t T, int32_t C, int32_t batch,
                       const void* w, float bias, int32_t k, float* wav, int64_t wav_ld, sb_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * SeamlessStreaming monotonic (EMMA) decoder pieces: PChooseLayer.forward (models/monotonic_decoder/p_choose.py:120-148).
+ * The energy projections are sb_gemm calls (Linear+ReLU x4); these two cover the pooling and the step probability.
+ *   sb_avgpool_time: y[b][j] = mean of x[b][j*ratio .. min((j+1)*ratio, T))   (AvgPool1d, ceil_mode=True), fp16
+ *   sb_pchoose:      p[h][s][j] = sigmoid((q_h[s].k_h[j]/8 + energy_bias)/temperature), q (S, H*64), k (Sp, H*64), p fp32
+ * ---------------------------------------------------------------------------------------------------------------- */
+int sb_avgpool_time(const void* x, void* y, int32_t batch, int32_t T, int32_t C, int32_t ratio, sb_stream_t stream);
+int sb_pchoose(const void* q_energy, const void* k_energy, float* p, int32_t S, int32_t Sp, int32_t heads,
+               float energy_bias, float temperature, sb_stream_t stream);
+
 /* small utilities */
 int sb_cast_f32_to_f16(const float* src, void* dst, int64_t n, sb_stream_t stream);
 int sb_fill_zero(void* dst, int64_t bytes, sb_stream_t stream);

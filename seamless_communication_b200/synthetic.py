@@ -344,3 +344,22 @@ def make_waveforms(batch: int, num_samples: int = 160000, seed: int = 1234, samp
             x = x + a * torch.sin(2 * math.pi * f * t + ph)
         out[b] = x.clamp_(-1.0, 1.0)
     return out
+
+
+def make_monotonic_state_dict(cfg: UnitYConfig, seed: int = 2, logit_scale: float = 4.0, embed_scale: float = 0.25,
+                              dec_gain: float = 4.0, energy_layers: int = 4, energy_bias: float = -0.5) -> Dict[str, torch.Tensor]:
+    """Random-init SeamlessStreaming monotonic text decoder (reference models/monotonic_decoder/builder.py:88-103
+    `dense_1b`): an NLLB decoder whose every layer carries a PChooseLayer (p_choose.py:48-148).  Parameter names follow
+    the module tree of `MonotonicDecoderModel` (text_decoder_frontend / text_decoder / final_proj)."""
+    base = make_unity_state_dict(cfg, seed=seed, logit_scale=logit_scale, with_t2u=False, embed_scale=embed_scale, dec_gain=dec_gain)
+    sd = {k: v for k, v in base.items() if k.startswith(("text_decoder", "final_proj"))}
+    I = _Init(seed + 1000)
+    M = cfg.model_dim
+    for i in range(cfg.dec_layers):
+        p = f"text_decoder.layers.{i}.p_choose_layer"
+        for br in ("q_energy_proj", "k_energy_proj"):
+            for l in range(energy_layers):
+                I.linear(f"{p}.{br}.layers.{2 * l}", M, M, gain=1.2)  # Linear at even indices, ReLU at odd ones; gain keeps p_choose inside (0,1)
+        I.sd[f"{p}.energy_bias"] = torch.full((1,), energy_bias)
+    sd.update(I.sd)
+    return sd

@@ -385,3 +385,32 @@ def test_full_width_properties_permutation_padding_determinism(small, ops):
     k = n2 // 2
     assert rel(inner_alone.buf.view(1, -1, M)[0, :k], ei[2, :k]) < 2e-3           # different tiling, same values
     assert torch.isfinite(e).all() and e.float().std() > 0.1
+
+
+# ------------------------------------------------------------------------------------------------ a17 monotonic decoder
+def test_monotonic_decoder_pchoose_and_policy_match_oracle():
+    from seamless_communication_b200.models.monotonic_decoder import load_monotonic_decoder_model
+    from seamless_communication_b200.streaming import MMATextDecoderPolicy
+    cfg = C.tiny_v2()
+    sd = S.make_monotonic_state_dict(cfg, seed=2)
+    toks = S.make_tokenizers(cfg)
+    model = load_monotonic_decoder_model("tiny_v2", state_dict=sd, tokenizers=toks)
+    uo = UnityOracle(cfg.to_dict(), sd, toks)
+    torch.manual_seed(4)
+    enc = torch.randn(1, 13, cfg.model_dim).half().float()
+    ids = torch.tensor([[3, toks[0].lang_index("spa"), 20, 30, 40, 50]])
+    dec, pc = model.decode(ids, enc.to(dev))
+    o_dec, o_pc = uo.monotonic_decoder(ids, enc)
+    assert pc.shape == o_pc.shape == (cfg.dec_layers, cfg.num_heads, 6, 7)   # ceil(13/2) pooled keys
+    assert rel(dec, o_dec) < 5e-3
+    assert (pc.cpu() - o_pc).abs().max() < 2e-2                               # probabilities in (0,1), sigmoid(e/0.2)
+    # streaming: the same READ/WRITE decisions chunk by chunk (prob compared with a margin around the threshold)
+    pol = MMATextDecoderPolicy(model, "spa", max_len_b=10)
+    written, o_target = [], []
+    for n, fin in ((5, False), (9, False), (13, True)):
+        new, finished = pol.policy(enc[:, :n].to(dev), fin)
+        o_new, o_fin = uo.emma_policy(enc[:, :n], [3, toks[0].lang_index("spa")], o_target, fin, max_len=10)
+        o_target += o_new
+        written += new
+        assert new == o_new and finished == o_fin
+    assert written == o_target and len(written) > 0
