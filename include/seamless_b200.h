@@ -149,13 +149,17 @@ int sb_embed_seq(const int32_t* ids, int32_t ids_ld, int32_t L, const void* embe
  *   qkv: fp16 [rows][3*dim] (q|k|v of the new token); kcache/vcache: fp16 [max_len][rows][dim];
  *   anc: int32 [rows][anc_ld], anc[r][t] = cache slot holding position t of row r's history (t < step);
  *   the new k/v are stored to slot r at position `step`.  out: fp16 [rows][dim]. */
-int sb_decode_self_attn(const void* qkv, void* kcache, void* vcache, const int32_t* anc, int32_t anc_ld,
+/* q|k|v of the new token come either as fp16 `qkv` or (qkv == NULL) as split-K partials of the qkv projection
+ * ([splits][slice_rows][3*dim] fp32 + the fp32 projection bias), reduced on the fly. */
+int sb_decode_self_attn(const void* qkv, const float* qkv_partials, int32_t splits, int64_t slice_rows,
+                        const float* qkv_bias, void* kcache, void* vcache, const int32_t* anc, int32_t anc_ld,
                         const int32_t* step_ptr, int32_t max_len, void* out, int32_t rows, int32_t heads,
                         sb_stream_t stream);
 /* cross-attention of one token per row against per-utterance static K/V: k/v fp16 [batch][s_enc][dim] (row stride
  * kv_ld), row r attends utterance r / beam. */
-int sb_decode_cross_attn(const void* q, const void* k, const void* v, int64_t kv_ld, const int32_t* enc_lens,
-                         int32_t s_enc, void* out, int32_t rows, int32_t beam, int32_t heads, sb_stream_t stream);
+int sb_decode_cross_attn(const void* q, const float* q_partials, int32_t splits, int64_t slice_rows, const float* q_bias,
+                         const void* k, const void* v, int64_t kv_ld, const int32_t* enc_lens, int32_t s_enc, void* out,
+                         int32_t rows, int32_t beam, int32_t heads, sb_stream_t stream);
 /* per row: log-softmax statistics and the top-K candidates of an fp32 logit row.
  *   cand_val [rows][K] = lprob, cand_idx [rows][K]; eos_lprob[rows] = lprob of eos; pad is never a candidate. */
 int sb_logits_topk(const float* logits, int64_t ld, int32_t rows, int32_t vocab, int32_t pad_idx, int32_t eos_idx,

@@ -54,8 +54,8 @@ PROTOTYPES = {
     "sb_embed_step": [c_p, i32, c_p, c_p, c_p, f32, c_p, i32, i32, c_p],
     "sb_step_advance": [c_p, c_p],
     "sb_embed_seq": [c_p, i32, i32, c_p, c_p, f32, c_p, i32, i32, c_p],
-    "sb_decode_self_attn": [c_p, c_p, c_p, c_p, i32, c_p, i32, c_p, i32, i32, c_p],
-    "sb_decode_cross_attn": [c_p, c_p, c_p, i64, c_p, i32, c_p, i32, i32, i32, c_p],
+    "sb_decode_self_attn": [c_p, c_p, i32, i64, c_p, c_p, c_p, c_p, i32, c_p, i32, c_p, i32, i32, c_p],
+    "sb_decode_cross_attn": [c_p, c_p, i32, i64, c_p, c_p, c_p, i64, c_p, i32, c_p, i32, i32, i32, c_p],
     "sb_logits_topk": [c_p, i64, i32, i32, i32, i32, i32, f32, i32, c_p, c_p, c_p, c_p],
     "sb_beam_step": [C.POINTER(BeamDesc), c_p],
     "sb_text_to_chars": [c_p, i32, i32, c_p, c_p, c_p, i32, i32, i32, i32, c_p, c_p, i32, c_p, c_p],

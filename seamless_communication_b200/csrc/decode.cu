@@ -118,11 +118,28 @@ __device__ __forceinline__ void attend_one(const elem_t* __restrict__ qp, int nk
   }
 }
 
-__global__ void __launch_bounds__(128) decode_self_attn_kernel(const elem_t* __restrict__ qkv, elem_t* __restrict__ kcache,
-                                                               elem_t* __restrict__ vcache, const int* __restrict__ anc,
-                                                               int anc_ld, const int* __restrict__ step_ptr, int max_len,
+// q / k / v of the new token either come as fp16 (`qkv`) or as split-K partial products of the projection
+// (`part`: [splits][slice_rows][3*dim] fp32, plus the projection bias): summing the slices here removes the separate
+// reduction pass between the skinny qkv GEMM and the attention.
+__device__ __forceinline__ void gather_head_vec(const float* __restrict__ part, int splits, long long slice_rows, long long ld,
+                                                const float* __restrict__ bias, long long row, int col0, elem_t* dst) {
+  const int lane = threadIdx.x & 31;
+  float2 acc = *reinterpret_cast<const float2*>(bias + col0 + 2 * lane);
+  for (int z = 0; z < splits; ++z) {
+    const float2 p = *reinterpret_cast<const float2*>(part + ((long long)z * slice_rows + row) * ld + col0 + 2 * lane);
+    acc.x += p.x; acc.y += p.y;
+  }
+  reinterpret_cast<__half2*>(dst)[lane] = __floats2half2_rn(acc.x, acc.y);
+}
+
+__global__ void __launch_bounds__(128) decode_self_attn_kernel(const elem_t* __restrict__ qkv, const float* __restrict__ part,
+                                                               int splits, long long slice_rows, const float* __restrict__ bias,
+                                                               elem_t* __restrict__ kcache, elem_t* __restrict__ vcache,
+                                                               const int* __restrict__ anc, int anc_ld,
+                                                               const int* __restrict__ step_ptr, int max_len,
                                                                elem_t* __restrict__ out, int rows, int heads) {
   extern __shared__ float sc_all[];  // [4][max_len] scores + [4][max_len] ancestor slots
+  __shared__ __align__(16) elem_t s_new[4][3][HD];
   pdl_trigger();
   pdl_wait();
   const int step = *step_ptr;
@@ -133,9 +150,17 @@ __global__ void __launch_bounds__(128) decode_self_attn_kernel(const elem_t* __r
   const int dim = heads * HD;
   float* sc = sc_all + warp * max_len;
   int* slots = reinterpret_cast<int*>(sc_all + 4 * max_len) + warp * max_len;
-  const elem_t* qp = qkv + (long long)r * 3 * dim + h * HD;
-  const elem_t* knew = qp + dim;
-  const elem_t* vnew = qp + 2 * dim;
+  const elem_t *qp, *knew, *vnew;
+  if (part != nullptr) {
+#pragma unroll
+    for (int t = 0; t < 3; ++t) gather_head_vec(part, splits, slice_rows, 3LL * dim, bias, r, t * dim + h * HD, s_new[warp][t]);
+    __syncwarp();
+    qp = s_new[warp][0]; knew = s_new[warp][1]; vnew = s_new[warp][2];
+  } else {
+    qp = qkv + (long long)r * 3 * dim + h * HD;
+    knew = qp + dim;
+    vnew = qp + 2 * dim;
+  }
   // persist the new K/V (slot r, position step)
   {
     elem_t* kd = kcache + ((long long)step * rows + r) * dim + h * HD;
@@ -155,11 +180,14 @@ __global__ void __launch_bounds__(128) decode_self_attn_kernel(const elem_t* __r
   attend_one(qp, step + 1, kptr, vptr, sc, out + (long long)r * dim + hoff);
 }
 
-__global__ void __launch_bounds__(128) decode_cross_attn_kernel(const elem_t* __restrict__ q, const elem_t* __restrict__ k,
+__global__ void __launch_bounds__(128) decode_cross_attn_kernel(const elem_t* __restrict__ q, const float* __restrict__ part,
+                                                                int splits, long long slice_rows, const float* __restrict__ bias,
+                                                                const elem_t* __restrict__ k,
                                                                 const elem_t* __restrict__ v, long long kv_ld,
                                                                 const int* __restrict__ enc_lens, int s_enc,
                                                                 elem_t* __restrict__ out, int rows, int beam, int heads) {
   extern __shared__ float sc_all[];  // [4][s_enc]
+  __shared__ __align__(16) elem_t s_q[4][HD];
   pdl_trigger();
   pdl_wait();
   const int warp = threadIdx.x >> 5;
@@ -174,7 +202,13 @@ __global__ void __launch_bounds__(128) decode_cross_attn_kernel(const elem_t* __
   const elem_t* vb = v + (long long)b * s_enc * kv_ld + h * HD;
   auto kptr = [&](int t) -> const elem_t* { return kb + (long long)t * kv_ld; };
   auto vptr = [&](int t) -> const elem_t* { return vb + (long long)t * kv_ld; };
-  attend_one(q + (long long)r * dim + h * HD, len, kptr, vptr, sc, out + (long long)r * dim + h * HD);
+  const elem_t* qp = q + (long long)r * dim + h * HD;
+  if (part != nullptr) {
+    gather_head_vec(part, splits, slice_rows, dim, bias, r, h * HD, s_q[warp]);
+    __syncwarp();
+    qp = s_q[warp];
+  }
+  attend_one(qp, len, kptr, vptr, sc, out + (long long)r * dim + h * HD);
 }
 
 // ------------------------------------------------------------------------------------------- log-softmax stats + top-K
@@ -438,29 +472,35 @@ extern "C" int sb_embed_seq(const int32_t* ids, int32_t ids_ld, int32_t L, const
   return SB_OK;
 }
 
-extern "C" int sb_decode_self_attn(const void* qkv, void* kcache, void* vcache, const int32_t* anc, int32_t anc_ld,
+extern "C" int sb_decode_self_attn(const void* qkv, const float* qkv_partials, int32_t splits, int64_t slice_rows,
+                                   const float* qkv_bias, void* kcache, void* vcache, const int32_t* anc, int32_t anc_ld,
                                    const int32_t* step_ptr, int32_t max_len, void* out, int32_t rows, int32_t heads,
                                    sb_stream_t stream) {
   using namespace sb;
-  SB_REQUIRE(qkv && kcache && vcache && anc && out && step_ptr && rows > 0 && heads > 0 && max_len > 0, SB_EINVAL,
-             "sb_decode_self_attn: bad args");
+  SB_REQUIRE((qkv || (qkv_partials && qkv_bias && splits >= 1)) && kcache && vcache && anc && out && step_ptr && rows > 0 &&
+                 heads > 0 && max_len > 0,
+             SB_EINVAL, "sb_decode_self_attn: bad args");
   size_t smem = (size_t)8 * max_len * sizeof(float);
   SB_REQUIRE(smem <= 48 * 1024, SB_ENOSUP, "sb_decode_self_attn: max_len %d too large", max_len);
   SB_CUDA_OK(launch_k(decode_self_attn_kernel, dim3(rows, (heads + 3) / 4), dim3(128), smem, (cudaStream_t)stream,
-                       (const elem_t*)qkv, (elem_t*)kcache, (elem_t*)vcache, (const int*)anc, (int)anc_ld, (const int*)step_ptr,
+                       (const elem_t*)qkv, qkv_partials, (int)splits, (long long)slice_rows, qkv_bias, (elem_t*)kcache,
+                       (elem_t*)vcache, (const int*)anc, (int)anc_ld, (const int*)step_ptr,
                        (int)max_len, (elem_t*)out, (int)rows, (int)heads));
   count_launch();
   return SB_OK;
 }
 
-extern "C" int sb_decode_cross_attn(const void* q, const void* k, const void* v, int64_t kv_ld, const int32_t* enc_lens,
+extern "C" int sb_decode_cross_attn(const void* q, const float* q_partials, int32_t splits, int64_t slice_rows,
+                                    const float* q_bias, const void* k, const void* v, int64_t kv_ld, const int32_t* enc_lens,
                                     int32_t s_enc, void* out, int32_t rows, int32_t beam, int32_t heads, sb_stream_t stream) {
   using namespace sb;
-  SB_REQUIRE(q && k && v && out && rows > 0 && heads > 0 && s_enc > 0 && beam > 0, SB_EINVAL, "sb_decode_cross_attn: bad args");
+  SB_REQUIRE((q || (q_partials && q_bias && splits >= 1)) && k && v && out && rows > 0 && heads > 0 && s_enc > 0 && beam > 0,
+             SB_EINVAL, "sb_decode_cross_attn: bad args");
   size_t smem = (size_t)4 * s_enc * sizeof(float);
   SB_REQUIRE(smem <= 48 * 1024, SB_ENOSUP, "sb_decode_cross_attn: s_enc %d too large", s_enc);
   SB_CUDA_OK(launch_k(decode_cross_attn_kernel, dim3(rows, (heads + 3) / 4), dim3(128), smem, (cudaStream_t)stream,
-                       (const elem_t*)q, (const elem_t*)k, (const elem_t*)v, (long long)kv_ld, (const int*)enc_lens, (int)s_enc,
+                       (const elem_t*)q, q_partials, (int)splits, (long long)slice_rows, q_bias, (const elem_t*)k,
+                       (const elem_t*)v, (long long)kv_ld, (const int*)enc_lens, (int)s_enc,
                        (elem_t*)out, (int)rows, (int)beam, (int)heads));
   count_launch();
   return SB_OK;

@@ -665,7 +665,7 @@ extern "C" int sb_gemm_splitk(const sb_gemm_t* g_in, int32_t splits, float* part
   g.bias = nullptr; g.act = SB_ACT_NONE; g.alpha = 1.f; g.gamma = 1.f; g.res1 = nullptr; g.res2 = nullptr;
   g.out = partials; g.out_ld = g.n; g.out_f32 = 1; g.out2 = nullptr; g.out_row0 = 0; g.seq_rows = 0;
   SB_REQUIRE(slice_rows >= g.m, SB_EINVAL, "sb_gemm_splitk: slice_rows (%lld) < m (%d)", (long long)slice_rows, g.m);
-  if (g.n >= 128) return sb::launch<128>(&g, (cudaStream_t)stream, splits, slice_rows);
+  // 64-wide tiles: twice the CTAs and half the (fp32) epilogue per CTA - these problems are latency bound
   return sb::launch<64>(&g, (cudaStream_t)stream, splits, slice_rows);
 }
 

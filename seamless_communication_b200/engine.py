@@ -261,22 +261,25 @@ class UnitYEngine:
         check(lib.sb_embed_step(st["seqs"].data_ptr(), st["ML"], st["step"].data_ptr(), w["text_embed"].data_ptr(),
                                 self.pos.data_ptr(), math.sqrt(M), x.buf.data_ptr(), R, M, stream), "sb_embed_step")
         self._ln(x, "text_decoder.layers.0.self_attn_layer_norm", out=h)
-        S_ATT, S_FFN = st["splits_attn"], st["splits_ffn"]
+        S_ATT, S_FFN, S_QKV, SR = st["splits_attn"], st["splits_ffn"], st["splits_qkv"], ops.slice_rows(R)
         for i in range(c.dec_layers):
             p = f"text_decoder.layers.{i}"
             nxt = f"text_decoder.layers.{i + 1}.self_attn_layer_norm" if i + 1 < c.dec_layers else "text_decoder.layer_norm"
-            qkv = self._lin(h, p + ".self_attn.qkv", 3 * M, out=st["qkv"])
-            check(lib.sb_decode_self_attn(qkv.buf.data_ptr(), st["kc"][i].data_ptr(), st["vc"][i].data_ptr(),
-                                          st["anc"].data_ptr(), st["ML"], st["step"].data_ptr(), st["ML"],
-                                          st["att"].buf.data_ptr(), R, H, stream), "sb_decode_self_attn")
+            # qkv / q projections also run split-K; their partials are reduced (+bias) inside the attention kernels
+            ops.gemm_splitk(h, w[p + ".self_attn.qkv.w"], 3 * M, S_QKV, st["part_qkv"])
+            check(lib.sb_decode_self_attn(None, st["part_qkv"].data_ptr(), S_QKV, SR, w[p + ".self_attn.qkv.b"].data_ptr(),
+                                          st["kc"][i].data_ptr(), st["vc"][i].data_ptr(), st["anc"].data_ptr(), st["ML"],
+                                          st["step"].data_ptr(), st["ML"], st["att"].buf.data_ptr(), R, H, stream),
+                  "sb_decode_self_attn")
             ops.gemm_splitk(st["att"], w[p + ".self_attn.output_proj.w"], M, S_ATT, part)
             ops.splitk_reduce_ln(part, S_ATT, w[p + ".self_attn.output_proj.b"], x, w[p + ".encoder_decoder_attn_layer_norm.w"],
                                  w[p + ".encoder_decoder_attn_layer_norm.b"], h)
-            q = self._lin(h, p + ".encoder_decoder_attn.q_proj", M, out=st["q"])
+            ops.gemm_splitk(h, w[p + ".encoder_decoder_attn.q_proj.w"], M, S_ATT, part)
             kv = st["cross_kv"][i].buf
-            check(lib.sb_decode_cross_attn(q.buf.data_ptr(), kv.data_ptr(), kv[:, M:].data_ptr(), kv.stride(0),
-                                           ops._p(st["enc_lens"]), st["S_enc"], st["att"].buf.data_ptr(), R, st["beam"], H,
-                                           stream), "sb_decode_cross_attn")
+            check(lib.sb_decode_cross_attn(None, part.data_ptr(), S_ATT, SR, w[p + ".encoder_decoder_attn.q_proj.b"].data_ptr(),
+                                           kv.data_ptr(), kv[:, M:].data_ptr(), kv.stride(0), ops._p(st["enc_lens"]),
+                                           st["S_enc"], st["att"].buf.data_ptr(), R, st["beam"], H, stream),
+                  "sb_decode_cross_attn")
             ops.gemm_splitk(st["att"], w[p + ".encoder_decoder_attn.output_proj.w"], M, S_ATT, part)
             ops.splitk_reduce_ln(part, S_ATT, w[p + ".encoder_decoder_attn.output_proj.b"], x, w[p + ".ffn_layer_norm.w"],
                                  w[p + ".ffn_layer_norm.b"], h)
@@ -322,6 +325,8 @@ class UnitYEngine:
         k_att, k_ffn = max(M // 64, 1), max(c.dec_ffn_dim // 64, 1)  # k-blocks of the two residual GEMM kinds
         st["splits_attn"] = max(1, min(4, k_att // 4))
         st["splits_ffn"] = max(1, min(8, k_ffn // 8))
+        st["splits_qkv"] = max(1, min(2, k_att // 8))
+        st["part_qkv"] = torch.empty((st["splits_qkv"] * ops.slice_rows(R), 3 * M), dtype=torch.float32, device=dev)
         st["partials"] = torch.empty((max(st["splits_attn"], st["splits_ffn"]) * ops.slice_rows(R), M), dtype=torch.float32,
                                      device=dev)
         st["logits"] = Seq(1, R, c.text_vocab, dtype=torch.float32, buf=torch.empty(

@@ -77,11 +77,11 @@ if __name__ == "__main__":
         out = torch.empty(R, M, device=dev).half()
         for step in (10, 50, 100):
             st = torch.tensor([step], dtype=torch.int32, device=dev)
-            us = timeit(lambda: lib.sb_decode_self_attn(qkv.data_ptr(), kc.data_ptr(), vc.data_ptr(), anc.data_ptr(), ML, st.data_ptr(), ML, out.data_ptr(), R, H, ops._stream()))
+            us = timeit(lambda: lib.sb_decode_self_attn(qkv.data_ptr(), None, 0, 0, None, kc.data_ptr(), vc.data_ptr(), anc.data_ptr(), ML, st.data_ptr(), ML, out.data_ptr(), R, H, ops._stream()))
             print(f"decode_self_attn step={step}: {us:.1f} us")
         kv = torch.randn(32 * 63, 2 * M, device=dev).half()
         q = torch.randn(R, M, device=dev).half()
-        us = timeit(lambda: lib.sb_decode_cross_attn(q.data_ptr(), kv.data_ptr(), kv[:, M:].data_ptr(), 2 * M, None, 63, out.data_ptr(), R, 5, H, ops._stream()))
+        us = timeit(lambda: lib.sb_decode_cross_attn(q.data_ptr(), None, 0, 0, None, kv.data_ptr(), kv[:, M:].data_ptr(), 2 * M, None, 63, out.data_ptr(), R, 5, H, ops._stream()))
         print(f"decode_cross_attn S=63: {us:.1f} us")
         x = Seq(1, R, M); x.buf.normal_()
         w = torch.ones(M, device=dev); b = torch.zeros(M, device=dev); y = x.like()
