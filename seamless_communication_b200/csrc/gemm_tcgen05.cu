@@ -147,7 +147,9 @@ struct TileCfg {
   // 0.38 us per 64-deep k-block = 4 dependent MMAs, independent of N, tools/gemm_timeline.py), while a 128xBNx16 MMA
   // keeps the tensor pipe busy for only BN/2 cycles.  The K loop therefore round-robins NACC independent accumulators
   // (summed in the epilogue) so that several MMA chains are in flight.
-  static constexpr int NACC = BN >= 128 ? 2 : 4;
+  // (Measured in round 1: with MMA issue already under elect.sync the extra accumulators bought nothing and cost
+  // epilogue TMEM reads, so NACC is 1; the mechanism stays for the 256-wide 2-CTA tiles planned next.)
+  static constexpr int NACC = 1;
   static constexpr int TMEM_COLS = NACC * BN < 32 ? 32 : NACC * BN;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + BN * 4;
   static constexpr int THREADS = 32 * (5 + STAGES);
@@ -182,7 +184,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   float* bias_s = (float*)(smem + STAGES * Cfg::STAGE_BYTES + 256);
 
   pdl_trigger();
-  if (threadIdx.x == 0) TL(0);
+  if (threadIdx.x == 0) {
+    TL(0);
+    // hide the descriptor fetch of the first TMA behind the barrier / TMEM setup
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW)) : "memory");
+    if (g.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmO)) : "memory");
+  }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = (g.m_fast ? blockIdx.y : blockIdx.x) * BN;
   const int m0 = (g.m_fast ? blockIdx.x : blockIdx.y) * BM;
