@@ -651,10 +651,22 @@ __global__ void gemm_ref_kernel(const elem_t* __restrict__ A, long long a_rows, 
 
 }  // namespace sb
 
-extern "C" int sb_gemm(const sb_gemm_t* g, sb_stream_t stream) {
-  int rc = sb::validate(g);
+extern "C" int sb_gemm(const sb_gemm_t* g_in, sb_stream_t stream) {
+  int rc = sb::validate(g_in);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
+  // Narrow-channel undilated convs (HiFi-GAN stages with C = 16/32): the taps of an output row are `taps` consecutive
+  // input rows, i.e. one contiguous run of taps*C elements when rows are dense.  Describing A as overlapping rows of
+  // that length (row pitch still C) turns `taps` nearly empty 64-deep k-blocks into ceil(taps*C/64) full ones.
+  sb_gemm_t gc;
+  const sb_gemm_t* g = g_in;
+  if (g_in->taps > 1 && g_in->dil == 1 && g_in->c_in < sb::BK && g_in->a_ld == g_in->c_in) {
+    gc = *g_in;
+    gc.c_in = g_in->taps * g_in->c_in;
+    gc.taps = 1;
+    gc.a_rows = g_in->a_rows - (g_in->taps - 1);  // windows starting later would run past the buffer: zero-filled instead
+    g = &gc;
+  }
   const long long mt = (g->m + sb::BM - 1) / sb::BM;
   auto tiles = [&](int bn) { return mt * ((g->n + bn - 1) / bn); };
   // largest N tile that still gives every SM two CTAs; fall back to smaller tiles for skinny problems

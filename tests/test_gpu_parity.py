@@ -88,6 +88,26 @@ def test_gemm_conv_mask_residual_dual_output(ops, taps, dil):
     assert full[1, o.PH + 33:].abs().max() == 0 and full[2].abs().max() == 0
 
 
+@pytest.mark.parametrize("taps,Cc", [(3, 16), (7, 16), (11, 32), (11, 8)])
+def test_gemm_narrow_channel_conv(ops, taps, Cc):
+    """C < 64 with dilation 1 takes the overlapping-row (K-collapsed) tensor-map path."""
+    from seamless_communication_b200.ops import Seq
+    torch.manual_seed(taps + Cc)
+    B, T, N = 2, 700, Cc
+    halo = (taps - 1) // 2
+    x = Seq(B, T, Cc, halo=halo + 2)
+    x.data().copy_((torch.randn(B, T, Cc, device=dev) * 0.5).half())
+    w = (torch.randn(N, taps * Cc, device=dev) * 0.1).half()
+    bias = torch.randn(N, device=dev)
+    o = ops.gemm(x, w, N, bias, taps=taps, act=ops.ACT_LRELU, slope=0.1)
+    r = ops.gemm(x, w, N, bias, taps=taps, act=ops.ACT_LRELU, slope=0.1, ref=True)
+    y = F.conv1d(x.data().float().transpose(1, 2), w.float().view(N, taps, Cc).permute(0, 2, 1), bias, padding=halo)
+    y = F.leaky_relu(y, 0.1).transpose(1, 2)
+    assert rel(o.data(), y) < 2e-3 and rel(o.data(), r.data()) < 2e-3
+    full = o.buf.float().view(B, o.Tp, N)
+    assert full[:, :o.PH].abs().sum() == 0 and full[:, o.PH + T:].abs().sum() == 0
+
+
 def test_gemm_glu_and_splitk(ops):
     from seamless_communication_b200.ops import Seq
     torch.manual_seed(5)
