@@ -142,6 +142,8 @@ int sb_dwconv_ln_silu(const void* x, void* y, const void* w, const float* ln_w, 
 int sb_embed_step(const int32_t* seqs, int32_t seq_ld, const int32_t* step_ptr, const void* embed, const void* pos_table,
                   float scale, void* x, int32_t rows, int32_t dim, sb_stream_t stream);
 int sb_step_advance(int32_t* step_ptr, sb_stream_t stream);
+/* hist[*step_ptr] = h (bytes_per_step each): records the decoder output state of every search step */
+int sb_store_step(const void* h, void* hist, const int32_t* step_ptr, int64_t bytes_per_step, sb_stream_t stream);
 /* embeds a full (rows, L) id matrix (teacher-forced pass): x[(r*L+t)] = embed[ids[r*ids_ld+t]]*scale + pos[t] */
 int sb_embed_seq(const int32_t* ids, int32_t ids_ld, int32_t L, const void* embed, const void* pos_table, float scale,
                  void* x, int32_t rows, int32_t dim, sb_stream_t stream);
@@ -180,6 +182,7 @@ typedef struct {
   const float* cand_val; const int32_t* cand_idx; const float* eos_lprob;
   int32_t* seqs; float* scores; int32_t* anc;  /* reordered in place */
   int32_t* fin_count; float* fin_score; int32_t* fin_len; int32_t* fin_seqs; int32_t* active;
+  int32_t* fin_anc;    /* [B][beam][max_len] or NULL: per finished hypothesis, the cache slot of every position */
   int32_t* n_active;   /* [1] number of sentences still searching (written every step) */
 } sb_beam_t;
 int sb_beam_step(const sb_beam_t* p, sb_stream_t stream);

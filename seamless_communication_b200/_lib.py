@@ -33,7 +33,7 @@ class BeamDesc(C.Structure):
         ("cand_val", c_p), ("cand_idx", c_p), ("eos_lprob", c_p),
         ("seqs", c_p), ("scores", c_p), ("anc", c_p),
         ("fin_count", c_p), ("fin_score", c_p), ("fin_len", c_p), ("fin_seqs", c_p), ("active", c_p),
-        ("n_active", c_p),
+        ("fin_anc", c_p), ("n_active", c_p),
     ]
 
 
@@ -53,6 +53,7 @@ PROTOTYPES = {
     "sb_dwconv_ln_silu": [c_p, c_p, c_p, c_p, c_p, i32, i32, i32, i32, c_p],
     "sb_embed_step": [c_p, i32, c_p, c_p, c_p, f32, c_p, i32, i32, c_p],
     "sb_step_advance": [c_p, c_p],
+    "sb_store_step": [c_p, c_p, c_p, i64, c_p],
     "sb_embed_seq": [c_p, i32, i32, c_p, c_p, f32, c_p, i32, i32, c_p],
     "sb_decode_self_attn": [c_p, c_p, i32, i64, c_p, c_p, c_p, c_p, i32, c_p, i32, c_p, i32, i32, c_p],
     "sb_decode_cross_attn": [c_p, c_p, i32, i64, c_p, c_p, c_p, i64, c_p, i32, c_p, i32, i32, i32, c_p],

@@ -402,6 +402,11 @@ __global__ void __launch_bounds__(128) beam_step_kernel(const sb_beam_t p) {
           int* dst = p.fin_seqs + ((long long)b * beam + fin) * ML;
           for (int t = 0; t <= step; ++t) dst[t] = p.seqs[(long long)row * ML + t];
           dst[step + 1] = tok;
+          if (p.fin_anc != nullptr) {  // cache slots holding the decoder states of this hypothesis, position by position
+            int* fa = p.fin_anc + ((long long)b * beam + fin) * ML;
+            for (int t = 0; t < step; ++t) fa[t] = p.anc[(long long)row * ML + t];
+            fa[step] = row;
+          }
           p.fin_len[b * beam + fin] = step + 2;
           p.fin_score[b * beam + fin] = best / powf((float)(step + 1), p.len_penalty);
           ++fin;
@@ -442,6 +447,15 @@ __global__ void __launch_bounds__(128) beam_step_kernel(const sb_beam_t p) {
       p.seqs[dst] = sv[i]; p.scores[dst] = cv[i]; p.anc[dst] = av[i];
     }
   }
+}
+
+// hist[step][...] = h: keeps the final-LayerNorm decoder state of every search step so that the states of the winning
+// hypothesis can be gathered afterwards instead of re-running the decoder teacher-forced (inference/generator.py:294-299)
+__global__ void store_step_kernel(const uint4* __restrict__ h, uint4* __restrict__ hist, const int* __restrict__ step_ptr, long long n16) {
+  pdl_trigger();
+  pdl_wait();
+  uint4* dst = hist + (long long)(*step_ptr) * n16;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (long long)gridDim.x * blockDim.x) dst[i] = h[i];
 }
 
 __global__ void step_advance_kernel(int* step_ptr) {
@@ -531,6 +545,15 @@ extern "C" int sb_beam_step(const sb_beam_t* p, sb_stream_t stream) {
 extern "C" int sb_step_advance(int32_t* step_ptr, sb_stream_t stream) {
   SB_REQUIRE(step_ptr != nullptr, SB_EINVAL, "sb_step_advance: null");
   SB_CUDA_OK(sb::launch_k(sb::step_advance_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, (int*)step_ptr));
+  sb::count_launch();
+  return SB_OK;
+}
+
+extern "C" int sb_store_step(const void* h, void* hist, const int32_t* step_ptr, int64_t bytes_per_step, sb_stream_t stream) {
+  SB_REQUIRE(h && hist && step_ptr && bytes_per_step > 0 && bytes_per_step % 16 == 0, SB_EINVAL, "sb_store_step: bad args");
+  const long long n16 = bytes_per_step / 16;
+  SB_CUDA_OK(sb::launch_k(sb::store_step_kernel, dim3((unsigned)((n16 + 255) / 256)), dim3(256), 0, (cudaStream_t)stream,
+                          (const uint4*)h, (uint4*)hist, (const int*)step_ptr, n16));
   sb::count_launch();
   return SB_OK;
 }

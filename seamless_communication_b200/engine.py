@@ -286,6 +286,7 @@ class UnitYEngine:
             t = self._lin(h, p + ".ffn.inner_proj", c.dec_ffn_dim, act=ACT_RELU, out=st["ffn"])
             ops.gemm_splitk(t, w[p + ".ffn.output_proj.w"], M, S_FFN, part)
             ops.splitk_reduce_ln(part, S_FFN, w[p + ".ffn.output_proj.b"], x, w[nxt + ".w"], w[nxt + ".b"], h)
+        check(lib.sb_store_step(h.buf.data_ptr(), st["hist"].data_ptr(), st["step"].data_ptr(), R * M * 2, stream), "sb_store_step")
         ops.gemm(h, w["text_embed"], c.text_vocab, None, out=st["logits"], out_f32=True)
 
     def _decoder_step_select(self, st):
@@ -337,6 +338,8 @@ class UnitYEngine:
         fin = dict(count=torch.zeros(B, dtype=I32, device=dev), score=torch.zeros((B, beam), device=dev),
                    len=torch.zeros((B, beam), dtype=I32, device=dev), seqs=torch.zeros((B, beam, ML), dtype=I32, device=dev),
                    active=torch.ones(B, dtype=I32, device=dev), n_active=torch.zeros((1,), dtype=I32, device=dev))
+        fin["anc"] = torch.zeros((B, beam, ML), dtype=I32, device=dev)
+        st["hist"] = torch.empty((ML, R, M), dtype=F16, device=dev)  # final-LN decoder state of every step
         st["fin"] = fin
         d = BeamDesc()
         d.batch, d.beam, d.max_len, d.vocab, d.K = B, beam, ML, c.text_vocab, K
@@ -345,6 +348,7 @@ class UnitYEngine:
         d.seqs, d.scores, d.anc = st["seqs"].data_ptr(), st["scores"].data_ptr(), st["anc"].data_ptr()
         d.fin_count, d.fin_score, d.fin_len = fin["count"].data_ptr(), fin["score"].data_ptr(), fin["len"].data_ptr()
         d.fin_seqs, d.active, d.n_active = fin["seqs"].data_ptr(), fin["active"].data_ptr(), fin["n_active"].data_ptr()
+        d.fin_anc = fin["anc"].data_ptr()
         st["beam_desc"] = d
         st["g_fwd"] = st["g_sel"] = None
         st["n_fwd"] = st["n_sel"] = 0
@@ -448,14 +452,35 @@ class UnitYEngine:
         scr = fin["score"].cpu().tolist()
         ln_ = fin["len"].cpu().tolist()
         sq = fin["seqs"].cpu()
-        results = []
+        results, best = [], []
         for bi in range(B):
             hyps = [(scr[bi][j], sq[bi, j, :ln_[bi][j]].tolist()) for j in range(cnt[bi])]
             order = sorted(range(len(hyps)), key=lambda j: -hyps[j][0])
             results.append([hyps[j] for j in order])
+            best.append(order[0] if order else -1)
+        st["best_fin"] = best
         st["enc_ptr"] = enc.buf.data_ptr()
         self._last_search_state = st
         return results
+
+    @torch.inference_mode()
+    def harvest_decoder_states(self, lengths: List[int]) -> Optional[Seq]:
+        """Decoder output states of each sentence's best hypothesis, gathered from the per-step history of the last
+        beam search (position t of a hypothesis lives in hist[t][slot_t]).  Same function of the same tokens as the
+        reference's teacher-forced re-run of the decoder over the winning sequence minus its final EOS
+        (inference/generator.py:281-299), without the second pass.  `lengths[b]` = len(hypothesis) - 1."""
+        st = getattr(self, "_last_search_state", None)
+        if st is None or any(j < 0 for j in st["best_fin"]):
+            return None
+        B, M, dev = st["B"], self.M, self.device
+        L = max(lengths)
+        sel = torch.tensor(st["best_fin"], dtype=torch.int64, device=dev)
+        slots = st["fin"]["anc"][torch.arange(B, device=dev), sel][:, :L].to(torch.int64)      # (B, L)
+        t_idx = torch.arange(L, device=dev)[None, :].expand(B, L)
+        out = st["hist"][t_idx, slots]                                                            # (B, L, M) row gather
+        lens = torch.tensor(lengths, dtype=I32, device=dev)
+        out = out * (t_idx < lens[:, None].to(torch.int64))[:, :, None].to(out.dtype)             # zero the padding rows
+        return Seq(B, L, M, lens=lens, buf=out.reshape(B * L, M).contiguous())
 
     # ------------------------------------------------------------------------------------------ a10 teacher-forced pass
     @torch.inference_mode()

@@ -69,6 +69,7 @@ class UnitYGenerator:
         self.text_decoder = text_tokenizer.create_decoder()
         self.unit_decoder = None
         self.unit_prefix_indices = None
+        self.reuse_decoder_states = True  # False: recompute them with the teacher-forced pass, as the reference does
         if unit_tokenizer is not None:
             if model.t2u_model is None:
                 raise ValueError("`model` does not have a T2U sub-model when `unit_tokenizer` is not None.")
@@ -110,7 +111,11 @@ class UnitYGenerator:
             text_seqs[i, :len(s)] = torch.tensor(s)
         text_seqs = text_seqs[:, :-1].contiguous().to(enc_out.device)  # "trim the final EOS" (generator.py:287)
         text_lens = torch.tensor([len(s) - 1 for s in text_seq_list], dtype=I32, device=enc_out.device)
-        dec = eng.decode_full(text_seqs, text_lens, enc, enc_lens)  # generator.py:294-299
+        # generator.py:294-299 re-runs the decoder teacher-forced over the winning sequences; the same states were
+        # already computed during the search and are gathered from its history instead (engine.harvest_decoder_states)
+        dec = eng.harvest_decoder_states([len(s) - 1 for s in text_seq_list]) if self.reuse_decoder_states else None
+        if dec is None:
+            dec = eng.decode_full(text_seqs, text_lens, enc, enc_lens)
         assert self.model.t2u_model is not None and self.unit_decoder is not None
         units, unit_lens, aux = eng.t2u(dec, text_seqs, duration_factor)
         # engine.t2u already applied argmax -> pad mask -> UnitTokenDecoder (generator.py:346-353) on device

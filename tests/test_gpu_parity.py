@@ -276,6 +276,28 @@ def test_decoder_and_beam_search_match_oracle(tiny, ops):
     assert (lg.float().cpu() - uo.project(o_dec)).abs().max() < 5e-2
 
 
+def test_harvested_decoder_states_equal_teacher_forced_pass(tiny):
+    from seamless_communication_b200.ops import Seq
+    cfg, eng = tiny["cfg"], tiny["model"].engine
+    torch.manual_seed(6)
+    M, S_enc = cfg.model_dim, 15
+    e = Seq(3, S_enc, M, buf=torch.randn(3 * S_enc, M, device=dev).half())
+    lens = torch.tensor([15, 9, 15], dtype=torch.int32, device=dev)
+    hyps = eng.beam_search(e, lens, [cfg.text_eos, tiny["toks"][0].lang_index("spa")], beam=5, soft_max=(1, 8))
+    seqs = [h[0][1] for h in hyps]
+    got = eng.harvest_decoder_states([len(s) - 1 for s in seqs])
+    L = max(len(s) for s in seqs)
+    ts = torch.zeros(3, L, dtype=torch.int64)
+    for i, s in enumerate(seqs):
+        ts[i, :len(s)] = torch.tensor(s)
+    tl = torch.tensor([len(s) - 1 for s in seqs], dtype=torch.int32, device=dev)
+    want = eng.decode_full(ts[:, :-1].contiguous().to(dev), tl, e, lens)
+    for i, s in enumerate(seqs):
+        n = len(s) - 1
+        assert rel(got.buf.view(3, -1, M)[i, :n], want.buf.view(3, -1, M)[i, :n]) < 5e-3  # incremental vs full-pass fp16 order
+        assert got.buf.view(3, -1, M)[i, n:].abs().sum() == 0
+
+
 def test_beam_search_ragged_encoder_and_early_eos(tiny):
     """Sentences with different encoder lengths, searched together, equal the same sentences searched alone."""
     from seamless_communication_b200.ops import Seq
