@@ -74,6 +74,8 @@ typedef struct {
   int32_t seq_halo;    /* PH */
   int32_t seq_len;     /* T when seq_lens == NULL */
   const int32_t* seq_lens; /* per-sequence valid lengths or NULL */
+  const void* prefetch;    /* optional: a device range (e.g. the next layer's weights) to pull into L2 while this GEMM runs */
+  int64_t prefetch_bytes;
 } sb_gemm_t;
 
 int sb_gemm(const sb_gemm_t* g, sb_stream_t stream);

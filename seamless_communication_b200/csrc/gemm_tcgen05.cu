@@ -50,6 +50,8 @@ struct GemmArgs {
   int m_fast;  // skinny-M problems: blockIdx.x walks the M tiles so CTAs sharing a weight tile are co-scheduled (L2 reuse)
   int kb_per_split;  // split-K: k-blocks per blockIdx.z slice (0 = no split)
   long long slice_rows;  // split-K: slice z writes rows [z*slice_rows, z*slice_rows + m) of out
+  const char* prefetch;  // weights of the kernel that follows: pulled into L2 by the idle epilogue warp during the main loop
+  long long prefetch_bytes;
 };
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
@@ -286,6 +288,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else {
     // ------------------------------------------------------------------ epilogue (warps 0..3)
     pdl_wait();  // residual reads / output writes below must not overtake the upstream kernel
+    if (warp == 0 && g.prefetch_bytes > 0) {
+      // latency-bound chains (decoder step): the next GEMM's weights do not depend on this kernel's result, so each CTA
+      // asks L2 for its share now; the next kernel's first TMA loads then hit L2 instead of paying an HBM round trip
+      // (UBLKPF is a uniform-datapath instruction: one elected lane issues, in 16 KB pieces of this CTA's contiguous share)
+      constexpr long long CH = 16384;
+      const long long cta = blockIdx.x + (long long)gridDim.x * (blockIdx.y + (long long)gridDim.y * blockIdx.z);
+      const long long ncta = (long long)gridDim.x * gridDim.y * gridDim.z;
+      const long long share = ((g.prefetch_bytes + ncta - 1) / ncta + 4095) / 4096 * 4096;
+      const long long lo = cta * share, hi = min(lo + share, g.prefetch_bytes);
+      if (elect_one()) {
+        for (long long o = lo; o < hi; o += CH)
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(g.prefetch + o), "r"((uint32_t)min(CH, hi - o)) : "memory");
+      }
+      __syncwarp();
+    }
     mbar_wait(tmem_full_bar, 0);
     if (threadIdx.x == 0) TL(4);
     tc_fence_after();
@@ -539,6 +556,7 @@ static void fill_args(const sb_gemm_t* g, GemmArgs* a) {
   a->out2 = (elem_t*)g->out2; a->out2_ld = g->out2_ld; a->out2_slope = g->out2_slope;
   a->out_row0 = g->out_row0;
   a->seq_rows = g->seq_rows; a->seq_halo = g->seq_halo; a->seq_len = g->seq_len; a->seq_lens = g->seq_lens;
+  a->prefetch = (const char*)g->prefetch; a->prefetch_bytes = g->prefetch ? g->prefetch_bytes / 4096 * 4096 : 0;
   a->tma_store = 0;
   a->kb_per_split = 0;
   a->slice_rows = 0;

@@ -16,6 +16,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -57,6 +58,9 @@ class UnitYEngine:
         if self.has_t2u:
             self._build_char_tables()
         self._graphs = {}
+        self._search_streams = []
+        self.search_groups = 1  # concurrent sentence groups in beam_search (see _search_group_count)
+        self.decode_prefetch = os.environ.get("SB_DECODE_PREFETCH", "1") != "0"
         self.graph_kernels = 0  # kernels executed through CUDA-graph replays (bench.py: gpu_launches)
 
     # ------------------------------------------------------------------------------------------ weight packing
@@ -262,29 +266,37 @@ class UnitYEngine:
                                 self.pos.data_ptr(), math.sqrt(M), x.buf.data_ptr(), R, M, stream), "sb_embed_step")
         self._ln(x, "text_decoder.layers.0.self_attn_layer_norm", out=h)
         S_ATT, S_FFN, S_QKV, SR = st["splits_attn"], st["splits_ffn"], st["splits_qkv"], ops.slice_rows(R)
+        pf = self.decode_prefetch  # each GEMM pulls the weights of the GEMM after it into L2 (latency-bound chain)
         for i in range(c.dec_layers):
             p = f"text_decoder.layers.{i}"
-            nxt = f"text_decoder.layers.{i + 1}.self_attn_layer_norm" if i + 1 < c.dec_layers else "text_decoder.layer_norm"
+            last = i + 1 == c.dec_layers
+            nxt = "text_decoder.layer_norm" if last else f"text_decoder.layers.{i + 1}.self_attn_layer_norm"
+            w_next = None if last else w[f"text_decoder.layers.{i + 1}.self_attn.qkv.w"]
             # qkv / q projections also run split-K; their partials are reduced (+bias) inside the attention kernels
-            ops.gemm_splitk(h, w[p + ".self_attn.qkv.w"], 3 * M, S_QKV, st["part_qkv"])
+            ops.gemm_splitk(h, w[p + ".self_attn.qkv.w"], 3 * M, S_QKV, st["part_qkv"],
+                            prefetch=w[p + ".self_attn.output_proj.w"] if pf else None)
             check(lib.sb_decode_self_attn(None, st["part_qkv"].data_ptr(), S_QKV, SR, w[p + ".self_attn.qkv.b"].data_ptr(),
                                           st["kc"][i].data_ptr(), st["vc"][i].data_ptr(), st["anc"].data_ptr(), st["ML"],
                                           st["step"].data_ptr(), st["ML"], st["att"].buf.data_ptr(), R, H, stream),
                   "sb_decode_self_attn")
-            ops.gemm_splitk(st["att"], w[p + ".self_attn.output_proj.w"], M, S_ATT, part)
+            ops.gemm_splitk(st["att"], w[p + ".self_attn.output_proj.w"], M, S_ATT, part,
+                            prefetch=w[p + ".encoder_decoder_attn.q_proj.w"] if pf else None)
             ops.splitk_reduce_ln(part, S_ATT, w[p + ".self_attn.output_proj.b"], x, w[p + ".encoder_decoder_attn_layer_norm.w"],
                                  w[p + ".encoder_decoder_attn_layer_norm.b"], h)
-            ops.gemm_splitk(h, w[p + ".encoder_decoder_attn.q_proj.w"], M, S_ATT, part)
+            ops.gemm_splitk(h, w[p + ".encoder_decoder_attn.q_proj.w"], M, S_ATT, part,
+                            prefetch=w[p + ".encoder_decoder_attn.output_proj.w"] if pf else None)
             kv = st["cross_kv"][i].buf
             check(lib.sb_decode_cross_attn(None, part.data_ptr(), S_ATT, SR, w[p + ".encoder_decoder_attn.q_proj.b"].data_ptr(),
                                            kv.data_ptr(), kv[:, M:].data_ptr(), kv.stride(0), ops._p(st["enc_lens"]),
                                            st["S_enc"], st["att"].buf.data_ptr(), R, st["beam"], H, stream),
                   "sb_decode_cross_attn")
-            ops.gemm_splitk(st["att"], w[p + ".encoder_decoder_attn.output_proj.w"], M, S_ATT, part)
+            ops.gemm_splitk(st["att"], w[p + ".encoder_decoder_attn.output_proj.w"], M, S_ATT, part,
+                            prefetch=w[p + ".ffn.inner_proj.w"] if pf else None)
             ops.splitk_reduce_ln(part, S_ATT, w[p + ".encoder_decoder_attn.output_proj.b"], x, w[p + ".ffn_layer_norm.w"],
                                  w[p + ".ffn_layer_norm.b"], h)
-            t = self._lin(h, p + ".ffn.inner_proj", c.dec_ffn_dim, act=ACT_RELU, out=st["ffn"])
-            ops.gemm_splitk(t, w[p + ".ffn.output_proj.w"], M, S_FFN, part)
+            t = self._lin(h, p + ".ffn.inner_proj", c.dec_ffn_dim, act=ACT_RELU, out=st["ffn"],
+                          prefetch=w[p + ".ffn.output_proj.w"] if pf else None)
+            ops.gemm_splitk(t, w[p + ".ffn.output_proj.w"], M, S_FFN, part, prefetch=w_next if pf else None)
             ops.splitk_reduce_ln(part, S_FFN, w[p + ".ffn.output_proj.b"], x, w[nxt + ".w"], w[nxt + ".b"], h)
         check(lib.sb_store_step(h.buf.data_ptr(), st["hist"].data_ptr(), st["step"].data_ptr(), R * M * 2, stream), "sb_store_step")
         ops.gemm(h, w["text_embed"], c.text_vocab, None, out=st["logits"], out_f32=True)
@@ -299,11 +311,11 @@ class UnitYEngine:
         check(lib.sb_beam_step(C.byref(st["beam_desc"]), stream), "sb_beam_step")
         check(lib.sb_step_advance(st["step"].data_ptr(), stream), "sb_step_advance")
 
-    def _search_state(self, B, S_enc, ML, beam, P, has_lens, use_graph):
+    def _search_state(self, B, S_enc, ML, beam, P, has_lens, use_graph, slot=0):
         """Static buffers + captured CUDA graphs of one decoder step, cached per problem shape so that repeated
         predict() calls replay the same graphs (the reference rebuilds its generator per call, translator.py:179-186;
         construction here stays cheap after the first call)."""
-        key = (B, S_enc, ML, beam, P, has_lens, use_graph)
+        key = (B, S_enc, ML, beam, P, has_lens, use_graph, slot)
         st = self._graphs.get(key)
         if st is not None:
             return st
@@ -373,21 +385,19 @@ class UnitYEngine:
             self._decoder_step_select(st)
         st["n_fwd"], st["n_sel"] = n1 - n0, ops.launch_count() - n1
 
-    @torch.inference_mode()
-    def beam_search(self, enc: Seq, enc_lens, prefix: List[int], beam=5, soft_max=(1, 200), hard_max=1024,
-                    len_penalty=1.0, unk_penalty=0.0, min_seq_len=1, use_graph=True, cross_kv=None):
-        """Device-resident beam search.  Returns per sentence the finished hypotheses [(score, ids)], best first
-        (semantics: fairseq2.cpp:1371-1608; see decode.cu).  `cross_kv` is ignored (kept for API stability): the
-        static cross-attention K/V of the cached search state are recomputed from `enc`."""
-        c, M, dev = self.cfg, self.M, self.device
-        B, S_enc = enc.B, enc.T
-        a, b = soft_max
-        ML = hard_max if a <= 0 else min(hard_max, int(a * S_enc) + b)  # fairseq2.cpp:1097-1105
-        P = len(prefix)
-        assert 1 <= P < ML
-        st = self._search_state(B, S_enc, ML, beam, P, enc_lens is not None, use_graph)
-        R, K, fin = st["R"], st["K"], st["fin"]
-        # (re)initialise the search state in place
+    def _search_reset(self, st, prefix):
+        fin, P = st["fin"], st["P"]
+        st["seqs"].zero_()
+        st["seqs"][:, :P] = torch.tensor(prefix, dtype=I32, device=self.device)
+        st["scores"].zero_()
+        st["anc"].copy_(st["anc_init"])
+        fin["count"].zero_(); fin["score"].fill_(-math.inf); fin["len"].zero_(); fin["active"].fill_(1)
+        fin["n_active"].fill_(st["B"])
+        st["step"].zero_()
+
+    def _search_prepare(self, st, enc: Seq, enc_lens, prefix, len_penalty, unk_penalty, min_seq_len, use_graph):
+        """(Re)initialise one cached search state in place for the sentences of `enc`; capture its graphs if needed."""
+        c, M = self.cfg, self.M
         st["unk_penalty"] = float(unk_penalty)
         d = st["beam_desc"]
         if (d.min_len, d.len_penalty) != (min_seq_len, len_penalty) or st.get("unk_cap") != float(unk_penalty):
@@ -398,56 +408,34 @@ class UnitYEngine:
             st["enc_lens"].copy_(enc_lens)
         for i in range(c.dec_layers):
             self._lin(enc, f"text_decoder.layers.{i}.encoder_decoder_attn.kv", 2 * M, out=st["cross_kv"][i])
-        st["seqs"].zero_()
-        st["seqs"][:, :P] = torch.tensor(prefix, dtype=I32, device=dev)
-        st["scores"].zero_()
-        st["anc"].copy_(st["anc_init"])
-        fin["count"].zero_(); fin["score"].fill_(-math.inf); fin["len"].zero_(); fin["active"].fill_(1)
-        fin["n_active"].fill_(B)
+        self._search_reset(st, prefix)
         if use_graph and st["g_fwd"] is None:
-            st["step"].zero_()
             self._capture(st)
-            # the warm-up touched position-0 cache rows and the search state: reset what it changed
-            st["seqs"].zero_()
-            st["seqs"][:, :P] = torch.tensor(prefix, dtype=I32, device=dev)
-            st["scores"].zero_()
-            st["anc"].copy_(st["anc_init"])
-            fin["count"].zero_(); fin["score"].fill_(-math.inf); fin["len"].zero_(); fin["active"].fill_(1)
-            fin["n_active"].fill_(B)
-        st["step"].zero_()
+            self._search_reset(st, prefix)  # the warm-up touched position-0 cache rows and the search state
 
-        def run_fwd():
-            if use_graph:
-                st["g_fwd"].replay(); self.graph_kernels += st["n_fwd"]
-            else:
-                self._decoder_step_forward(st)
-
-        def run_sel():
-            if use_graph:
+    def _search_step(self, st, use_graph, select=True):
+        if use_graph:
+            st["g_fwd"].replay(); self.graph_kernels += st["n_fwd"]
+            if select:
                 st["g_sel"].replay(); self.graph_kernels += st["n_sel"]
-            else:
+        else:
+            self._decoder_step_forward(st)
+            if select:
                 self._decoder_step_select(st)
 
-        # bootstrap (fairseq2.cpp:1162-1247): feed prefix[:-1], score prefix[1:]
-        lib = _lib.load()
-        for i in range(P - 1):
-            run_fwd()
-            # lprob of the next prefix token: the top-K kernel reports the lprob of its `eos_idx` argument
-            check(lib.sb_logits_topk(st["logits"].buf.data_ptr(), st["logits"].buf.stride(0), R, c.text_vocab, c.text_pad,
-                                     prefix[i + 1], c.text_unk, 0.0, K, st["cand_val"].data_ptr(), st["cand_idx"].data_ptr(),
-                                     st["eos_lprob"].data_ptr(), ops._stream()), "sb_logits_topk")
-            st["scores"][:, i + 1] = st["scores"][:, i] + st["eos_lprob"]
-            check(lib.sb_step_advance(st["step"].data_ptr(), ops._stream()), "sb_step_advance")
-        n_steps = ML - 1 - (P - 1)
-        done = 0
-        while done < n_steps:
-            chunk = min(32, n_steps - done)
-            for _ in range(chunk):
-                run_fwd()
-                run_sel()
-            done += chunk
-            if done < n_steps and int(fin["n_active"].item()) == 0:
-                break
+    def _search_bootstrap_step(self, st, prefix, i, use_graph):
+        """fairseq2.cpp:1162-1247: feed prefix[i], score prefix[i+1] (the top-K kernel reports the lprob of its
+        `eos_idx` argument, here the next prefix token)."""
+        lib, c = _lib.load(), self.cfg
+        self._search_step(st, use_graph, select=False)
+        check(lib.sb_logits_topk(st["logits"].buf.data_ptr(), st["logits"].buf.stride(0), st["R"], c.text_vocab, c.text_pad,
+                                 prefix[i + 1], c.text_unk, 0.0, st["K"], st["cand_val"].data_ptr(), st["cand_idx"].data_ptr(),
+                                 st["eos_lprob"].data_ptr(), ops._stream()), "sb_logits_topk")
+        st["scores"][:, i + 1] = st["scores"][:, i] + st["eos_lprob"]
+        check(lib.sb_step_advance(st["step"].data_ptr(), ops._stream()), "sb_step_advance")
+
+    def _search_collect(self, st):
+        fin, B = st["fin"], st["B"]
         cnt = fin["count"].cpu().tolist()
         scr = fin["score"].cpu().tolist()
         ln_ = fin["len"].cpu().tolist()
@@ -459,8 +447,86 @@ class UnitYEngine:
             results.append([hyps[j] for j in order])
             best.append(order[0] if order else -1)
         st["best_fin"] = best
-        st["enc_ptr"] = enc.buf.data_ptr()
-        self._last_search_state = st
+        return results
+
+    def _search_group_count(self, B: int) -> int:
+        """Sentences are searched independently (no cross-sentence op), so the batch can be cut into groups
+        whose step chains run concurrently on separate streams.  Measured on B200 at 32 sentences x beam 5 this is
+        slower (232 / 274 / 326 / 368 ms for 1-4 groups: every group re-reads the weights and the chains contend for
+        the same SMs), so the default is one group; SB_SEARCH_GROUPS overrides."""
+        g = int(os.environ.get("SB_SEARCH_GROUPS", "0")) or self.search_groups
+        return max(1, min(g, B // 4)) if B >= 8 else 1
+
+    @torch.inference_mode()
+    def beam_search(self, enc: Seq, enc_lens, prefix: List[int], beam=5, soft_max=(1, 200), hard_max=1024,
+                    len_penalty=1.0, unk_penalty=0.0, min_seq_len=1, use_graph=True, cross_kv=None):
+        """Device-resident beam search.  Returns per sentence the finished hypotheses [(score, ids)], best first
+        (semantics: fairseq2.cpp:1371-1608; see decode.cu).  `cross_kv` is ignored (kept for API stability): the
+        static cross-attention K/V of the cached search state are recomputed from `enc`."""
+        M = self.M
+        B, S_enc = enc.B, enc.T
+        a, b = soft_max
+        ML = hard_max if a <= 0 else min(hard_max, int(a * S_enc) + b)  # fairseq2.cpp:1097-1105
+        P = len(prefix)
+        assert 1 <= P < ML
+        assert enc.PH == 0 and enc.Tp == enc.T, "encoder output must be a halo-free Seq"
+        G = self._search_group_count(B)
+        bounds = [(B * g) // G for g in range(G + 1)]
+        main = torch.cuda.current_stream()
+        while len(self._search_streams) < G:
+            self._search_streams.append(torch.cuda.Stream())
+        groups = []
+        for g in range(G):
+            b0, b1 = bounds[g], bounds[g + 1]
+            st = self._search_state(b1 - b0, S_enc, ML, beam, P, enc_lens is not None, use_graph, slot=g)
+            e = enc if G == 1 else Seq(b1 - b0, S_enc, M, buf=enc.buf[b0 * S_enc:b1 * S_enc])
+            self._search_prepare(st, e, None if enc_lens is None else enc_lens[b0:b1], prefix, len_penalty, unk_penalty,
+                                 min_seq_len, use_graph)
+            st["b0"] = b0
+            groups.append(st)
+        n_steps = ML - 1 - (P - 1)
+        if G == 1:
+            st = groups[0]
+            for i in range(P - 1):
+                self._search_bootstrap_step(st, prefix, i, use_graph)
+            done = 0
+            while done < n_steps:
+                chunk = min(32, n_steps - done)
+                for _ in range(chunk):
+                    self._search_step(st, use_graph)
+                done += chunk
+                if done < n_steps and int(st["fin"]["n_active"].item()) == 0:
+                    break
+        else:
+            streams = self._search_streams[:G]
+            for s in streams:
+                s.wait_stream(main)
+            for i in range(P - 1):
+                for st, s in zip(groups, streams):
+                    with torch.cuda.stream(s):
+                        self._search_bootstrap_step(st, prefix, i, use_graph)
+            live, done = list(range(G)), 0
+            while done < n_steps and live:
+                chunk = min(32, n_steps - done)
+                for _ in range(chunk):
+                    for g in live:  # interleaved so that the groups' step chains overlap on the device
+                        with torch.cuda.stream(streams[g]):
+                            self._search_step(groups[g], use_graph)
+                done += chunk
+                if done < n_steps:
+                    still = []
+                    for g in live:
+                        with torch.cuda.stream(streams[g]):
+                            if int(groups[g]["fin"]["n_active"].item()) != 0:
+                                still.append(g)
+                    live = still
+            for s in streams:
+                main.wait_stream(s)
+        results = []
+        for st in groups:
+            results.extend(self._search_collect(st))
+        groups[0]["enc_ptr"] = enc.buf.data_ptr() if G == 1 else None
+        self._last_search_states = groups
         return results
 
     @torch.inference_mode()
@@ -469,15 +535,19 @@ class UnitYEngine:
         beam search (position t of a hypothesis lives in hist[t][slot_t]).  Same function of the same tokens as the
         reference's teacher-forced re-run of the decoder over the winning sequence minus its final EOS
         (inference/generator.py:281-299), without the second pass.  `lengths[b]` = len(hypothesis) - 1."""
-        st = getattr(self, "_last_search_state", None)
-        if st is None or any(j < 0 for j in st["best_fin"]):
+        groups = getattr(self, "_last_search_states", None)
+        if not groups or any(j < 0 for st in groups for j in st["best_fin"]):
             return None
-        B, M, dev = st["B"], self.M, self.device
-        L = max(lengths)
-        sel = torch.tensor(st["best_fin"], dtype=torch.int64, device=dev)
-        slots = st["fin"]["anc"][torch.arange(B, device=dev), sel][:, :L].to(torch.int64)      # (B, L)
-        t_idx = torch.arange(L, device=dev)[None, :].expand(B, L)
-        out = st["hist"][t_idx, slots]                                                            # (B, L, M) row gather
+        M, dev = self.M, self.device
+        B, L = len(lengths), max(lengths)
+        t_idx = torch.arange(L, device=dev)[None, :]
+        parts = []
+        for st in groups:
+            Bg = st["B"]
+            sel = torch.tensor(st["best_fin"], dtype=torch.int64, device=dev)
+            slots = st["fin"]["anc"][torch.arange(Bg, device=dev), sel][:, :L].to(torch.int64)  # (Bg, L)
+            parts.append(st["hist"][t_idx.expand(Bg, L), slots])                                 # (Bg, L, M) row gather
+        out = parts[0] if len(parts) == 1 else torch.cat(parts)
         lens = torch.tensor(lengths, dtype=I32, device=dev)
         out = out * (t_idx < lens[:, None].to(torch.int64))[:, :, None].to(out.dtype)             # zero the padding rows
         return Seq(B, L, M, lens=lens, buf=out.reshape(B * L, M).contiguous())
@@ -489,7 +559,8 @@ class UnitYEngine:
         c, M, H = self.cfg, self.M, self.H
         B, L = text_seqs.shape
         if cross_kv is None:
-            st = getattr(self, "_last_search_state", None)
+            sts = getattr(self, "_last_search_states", None)
+            st = sts[0] if sts and len(sts) == 1 else None
             cross_kv = st["cross_kv"] if (st is not None and st.get("enc_ptr") == enc.buf.data_ptr()) else self._cross_kv(enc)
         xb = ops.embed_seq(text_seqs.to(I32).contiguous(), self.w["text_embed"], self.pos, math.sqrt(M), M)
         x = Seq(B, L, M, lens=text_lens, buf=xb)
@@ -646,20 +717,21 @@ class VocoderEngine:
               "sb_vocoder_embed")
         ch = c.upsample_initial_channel
         act = ops.gemm(x0, w["conv_pre.w"], ch, w["conv_pre.b"], taps=7, act=ACT_LRELU, slope=0.1)  # lrelu fused for ups[0]
+        # every buffer below is fully written by a masked sb_gemm except its outermost halo rows (zero="edges")
         nk = len(c.resblock_kernel_sizes)
         nstage = len(c.upsample_rates)
         for i, u in enumerate(c.upsample_rates):
             cout = ch // (2 ** (i + 1))
             # ConvTranspose1d as a 3-tap GEMM producing u*cout values per input frame == u output frames of cout
-            up_raw = Seq(act.B, act.T, u * cout, act.PH, act.Tp)
-            up_act = Seq(act.B, act.T, u * cout, act.PH, act.Tp)
+            up_raw = Seq(act.B, act.T, u * cout, act.PH, act.Tp, zero="edges")
+            up_act = Seq(act.B, act.T, u * cout, act.PH, act.Tp, zero="edges")
             ops.gemm(act, w[f"ups.{i}.w"], u * cout, w[f"ups.{i}.b"], taps=3, out=up_raw, out2=up_act, out2_slope=0.1)
             T, PHn, Tp = act.T * u, act.PH * u, act.Tp * u
             x_raw = Seq(B, T, cout, PHn, Tp, buf=up_raw.buf.view(B * Tp, cout))
             x_act = Seq(B, T, cout, PHn, Tp, buf=up_act.buf.view(B * Tp, cout))
             last_slope = 0.01 if i == nstage - 1 else 0.1  # F.leaky_relu default slope before conv_post (hifigan.py:192)
             xs = None
-            nxt_act = Seq(B, T, cout, PHn, Tp)
+            nxt_act = Seq(B, T, cout, PHn, Tp, zero="edges")
             for j, (rk, dil) in enumerate(zip(c.resblock_kernel_sizes, c.resblock_dilation_sizes)):
                 rb = i * nk + j
                 y_raw, y_act = x_raw, x_act
@@ -668,7 +740,7 @@ class VocoderEngine:
                                   dil=d, act=ACT_LRELU, slope=0.1)
                     lastpair = di == len(dil) - 1
                     if not lastpair:
-                        n_raw, n_act = Seq(B, T, cout, PHn, Tp), Seq(B, T, cout, PHn, Tp)
+                        n_raw, n_act = Seq(B, T, cout, PHn, Tp, zero="edges"), Seq(B, T, cout, PHn, Tp, zero="edges")
                         ops.gemm(t1, w[f"resblocks.{rb}.convs2.{di}.w"], cout, w[f"resblocks.{rb}.convs2.{di}.b"], taps=rk,
                                  res1=y_raw, out=n_raw, out2=n_act, out2_slope=0.1)
                         y_raw, y_act = n_raw, n_act
@@ -676,7 +748,7 @@ class VocoderEngine:
                         # xs (+)= resblock output; the last resblock also applies the 1/num_kernels mean and the
                         # leaky-relu that feeds the next stage (hifigan.py:186-192)
                         lastblock = j == nk - 1
-                        acc = Seq(B, T, cout, PHn, Tp)
+                        acc = Seq(B, T, cout, PHn, Tp, zero="edges")
                         ops.gemm(t1, w[f"resblocks.{rb}.convs2.{di}.w"], cout, w[f"resblocks.{rb}.convs2.{di}.b"], taps=rk,
                                  res1=y_raw, res2=xs, gamma=(1.0 / nk) if lastblock else 1.0, out=acc,
                                  out2=nxt_act if lastblock else None, out2_slope=last_slope)

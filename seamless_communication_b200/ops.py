@@ -56,7 +56,7 @@ class Seq:
 
 def gemm(a: Seq, w: torch.Tensor, n: int, bias=None, *, taps=1, dil=1, act=ACT_NONE, slope=0.0, glu=False, alpha=1.0,
          gamma=1.0, res1: Optional[Seq] = None, res2: Optional[Seq] = None, out: Optional[Seq] = None,
-         out2: Optional[Seq] = None, out2_slope=0.0, mask=None, out_f32=False, ref=False) -> Seq:
+         out2: Optional[Seq] = None, out2_slope=0.0, mask=None, out_f32=False, ref=False, prefetch: Optional[torch.Tensor] = None) -> Seq:
     """Linear (taps=1) or 'same'-padded Conv1d (odd taps, dilation dil) over a Seq; output shares a's layout."""
     lib = _lib.load()
     halo = (taps - 1) * dil // 2
@@ -83,6 +83,8 @@ def gemm(a: Seq, w: torch.Tensor, n: int, bias=None, *, taps=1, dil=1, act=ACT_N
     d.out_row0 = a.PH
     if mask:
         d.seq_rows, d.seq_halo, d.seq_len, d.seq_lens = a.Tp, a.PH, a.T, _p(a.lens)
+    if prefetch is not None:
+        d.prefetch, d.prefetch_bytes = prefetch.data_ptr(), prefetch.numel() * prefetch.element_size()
     fn = lib.sb_gemm_ref if ref else lib.sb_gemm
     check(fn(C.byref(d), _stream()), "sb_gemm")
     return out
@@ -113,7 +115,8 @@ def slice_rows(rows: int) -> int:
     return (rows + 127) // 128 * 128
 
 
-def gemm_splitk(a: Seq, w: torch.Tensor, n: int, splits: int, partials: torch.Tensor) -> None:
+def gemm_splitk(a: Seq, w: torch.Tensor, n: int, splits: int, partials: torch.Tensor,
+                prefetch: Optional[torch.Tensor] = None) -> None:
     """Raw fp32 partial products of a (dense) Seq against w into partials[(z*slice_rows(rows) + r), n]."""
     lib = _lib.load()
     assert a.PH == 0 and a.Tp == a.T
@@ -121,6 +124,8 @@ def gemm_splitk(a: Seq, w: torch.Tensor, n: int, splits: int, partials: torch.Te
     d.a, d.a_rows, d.a_ld, d.c_in, d.taps, d.dil, d.a_row0 = a.buf.data_ptr(), a.B * a.T, a.buf.stride(0), a.C, 1, 1, 0
     d.w, d.n, d.m = w.data_ptr(), n, a.B * a.T
     d.out = partials.data_ptr()  # validated as non-null; sb_gemm_splitk overrides the epilogue fields
+    if prefetch is not None:
+        d.prefetch, d.prefetch_bytes = prefetch.data_ptr(), prefetch.numel() * prefetch.element_size()
     check(lib.sb_gemm_splitk(C.byref(d), splits, partials.data_ptr(), slice_rows(a.B * a.T), _stream()), "sb_gemm_splitk")
 
 

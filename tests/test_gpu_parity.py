@@ -298,6 +298,30 @@ def test_harvested_decoder_states_equal_teacher_forced_pass(tiny):
         assert got.buf.view(3, -1, M)[i, n:].abs().sum() == 0
 
 
+def test_beam_search_sentence_groups_on_streams_equal_single_group(tiny, monkeypatch):
+    """beam_search cuts the batch into sentence groups stepped concurrently on separate streams; hypotheses, scores and
+    harvested decoder states must not depend on the grouping."""
+    from seamless_communication_b200.ops import Seq
+    cfg, eng = tiny["cfg"], tiny["model"].engine
+    torch.manual_seed(11)
+    M, S_enc, B = cfg.model_dim, 10, 9
+    e = Seq(B, S_enc, M, buf=torch.randn(B * S_enc, M, device=dev).half())
+    lens = torch.tensor([10, 4, 10, 7, 10, 10, 2, 9, 10], dtype=torch.int32, device=dev)
+    prefix = [cfg.text_eos, tiny["toks"][0].lang_index("spa")]
+    out = {}
+    for g in (1, 2, 3):
+        monkeypatch.setenv("SB_SEARCH_GROUPS", str(g))
+        hyps = eng.beam_search(e, lens, prefix, beam=4, soft_max=(1, 6))
+        states = eng.harvest_decoder_states([len(h[0][1]) - 1 for h in hyps])
+        out[g] = (hyps, states.buf.clone())
+    assert len(eng._last_search_states) == 2  # 9 sentences: at most B // 4 groups
+    for g in (2, 3):
+        for h1, hg in zip(out[1][0], out[g][0]):
+            assert [x[1] for x in h1] == [x[1] for x in hg]
+            assert np.allclose([x[0] for x in h1], [x[0] for x in hg], rtol=0, atol=1e-6)
+        assert torch.equal(out[1][1], out[g][1])
+
+
 def test_beam_search_ragged_encoder_and_early_eos(tiny):
     """Sentences with different encoder lengths, searched together, equal the same sentences searched alone."""
     from seamless_communication_b200.ops import Seq
