@@ -224,6 +224,23 @@ int sb_unit_argmax(const float* logits, int64_t ld, int32_t rows_per_seq, int32_
 int sb_vocoder_embed(const int32_t* units, int32_t U, int32_t batch, const void* dict, int32_t dict_dim,
                      const void* lang, int32_t lang_dim, const int32_t* lang_idx, const void* spkr, int32_t spkr_dim,
                      const int32_t* spkr_idx, void* x, int32_t x_rows, int32_t x_halo, sb_stream_t stream);
+/* One whole HiFi-GAN ResBlock (models/vocoder/hifigan.py:33-121: three (convs1[d], convs2) pairs with leaky-relu and
+ * residual adds) on a sequence-layout activation with 16 or 32 channels, fused in shared memory:
+ *   out  = (resblock(x) + res2) * gamma        res2 = running sum over the generator's ResBlocks or NULL
+ *   out2 = leaky_relu(out, out2_slope)         optional (the activation that feeds the next stage, hifigan.py:183/192)
+ * Weights are the folded weight-norm kernels in sb_gemm conv layout (C, kernel_size * C), biases fp32.
+ * Every row of `out` / `out2` that belongs to a sequence or its halo is written (halo rows with zeros). */
+typedef struct {
+  const void* x; const void* res2; void* out; void* out2;
+  const void* w1[3]; const float* b1[3];   /* convs1: dilation[i] */
+  const void* w2[3]; const float* b2[3];   /* convs2: dilation 1 */
+  int32_t dilation[3];
+  int32_t channels, kernel_size;
+  int32_t batch, T, rows_per_seq, halo;    /* sequence layout: data rows [halo, halo + T) of each rows_per_seq block */
+  float slope;                             /* leaky-relu slope inside the block (hifigan.py:12 LRELU_SLOPE) */
+  float gamma, out2_slope;
+} sb_resblock_t;
+int sb_hifigan_resblock(const sb_resblock_t* r, sb_stream_t stream);
 /* final conv_post (C->1, k7) + tanh on CUDA cores: wav fp32 [B][T] from lrelu'ed activations in sequence layout */
 int sb_conv_post_tanh(const void* x, int32_t x_rows, int32_t x_halo, int32_t T, int32_t C, int32_t batch,
                       const void* w, float bias, int32_t k, float* wav, int64_t wav_ld, sb_stream_t stream);

@@ -27,6 +27,16 @@ class GemmDesc(C.Structure):
     ]
 
 
+class ResblockDesc(C.Structure):
+    _fields_ = [
+        ("x", c_p), ("res2", c_p), ("out", c_p), ("out2", c_p),
+        ("w1", c_p * 3), ("b1", c_p * 3), ("w2", c_p * 3), ("b2", c_p * 3),
+        ("dilation", i32 * 3), ("channels", i32), ("kernel_size", i32),
+        ("batch", i32), ("T", i32), ("rows_per_seq", i32), ("halo", i32),
+        ("slope", f32), ("gamma", f32), ("out2_slope", f32),
+    ]
+
+
 class BeamDesc(C.Structure):
     _fields_ = [
         ("batch", i32), ("beam", i32), ("max_len", i32), ("vocab", i32), ("K", i32),
@@ -64,6 +74,7 @@ PROTOTYPES = {
     "sb_upsample_add": [c_p, i32, i32, i32, c_p, c_p, i32, i32, i32, i32, i32, c_p, c_p, c_p, c_p, i32, f32, c_p, c_p],
     "sb_durations": [c_p, i32, i32, c_p, f32, i32, c_p, i32, i32, f32, c_p, c_p],
     "sb_unit_argmax": [c_p, i64, i32, i32, i32, i32, i32, c_p, i32, i32, c_p, c_p],
+    "sb_hifigan_resblock": [c_p, c_p],
     "sb_vocoder_embed": [c_p, i32, i32, c_p, i32, c_p, i32, c_p, c_p, i32, c_p, c_p, i32, i32, c_p],
     "sb_conv_post_tanh": [c_p, i32, i32, i32, i32, i32, c_p, f32, i32, c_p, i64, c_p],
     "sb_avgpool_time": [c_p, c_p, i32, i32, i32, i32, c_p],

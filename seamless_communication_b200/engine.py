@@ -656,6 +656,7 @@ class VocoderEngine:
     def __init__(self, cfg: VocoderConfig, state_dict: Dict[str, torch.Tensor], device="cuda"):
         _lib.require_cuda()
         self.cfg, self.device = cfg, torch.device(device)
+        self.fused_resblocks = os.environ.get("SB_FUSED_RESBLOCK", "1") != "0"  # 16/32-channel stages: resblock.cu
         self._pack(state_dict)
 
     def _pack(self, sd):
@@ -723,15 +724,33 @@ class VocoderEngine:
         for i, u in enumerate(c.upsample_rates):
             cout = ch // (2 ** (i + 1))
             # ConvTranspose1d as a 3-tap GEMM producing u*cout values per input frame == u output frames of cout
-            up_raw = Seq(act.B, act.T, u * cout, act.PH, act.Tp, zero="edges")
-            up_act = Seq(act.B, act.T, u * cout, act.PH, act.Tp, zero="edges")
-            ops.gemm(act, w[f"ups.{i}.w"], u * cout, w[f"ups.{i}.b"], taps=3, out=up_raw, out2=up_act, out2_slope=0.1)
             T, PHn, Tp = act.T * u, act.PH * u, act.Tp * u
-            x_raw = Seq(B, T, cout, PHn, Tp, buf=up_raw.buf.view(B * Tp, cout))
-            x_act = Seq(B, T, cout, PHn, Tp, buf=up_act.buf.view(B * Tp, cout))
             last_slope = 0.01 if i == nstage - 1 else 0.1  # F.leaky_relu default slope before conv_post (hifigan.py:192)
-            xs = None
             nxt_act = Seq(B, T, cout, PHn, Tp, zero="edges")
+            fused = self.fused_resblocks and cout in (16, 32) and all(
+                len(dl) == 3 and rk % 2 == 1 and rk <= 11 and (rk - 1) // 2 * max(dl) <= 32
+                for rk, dl in zip(c.resblock_kernel_sizes, c.resblock_dilation_sizes))
+            up_raw = Seq(act.B, act.T, u * cout, act.PH, act.Tp, zero="edges")
+            up_act = None if fused else Seq(act.B, act.T, u * cout, act.PH, act.Tp, zero="edges")
+            ops.gemm(act, w[f"ups.{i}.w"], u * cout, w[f"ups.{i}.b"], taps=3, out=up_raw, out2=up_act, out2_slope=0.1)
+            x_raw = Seq(B, T, cout, PHn, Tp, buf=up_raw.buf.view(B * Tp, cout))
+            if fused:
+                # narrow stages: each ResBlock is one kernel that keeps its time tile in shared memory (resblock.cu)
+                xs = None
+                for j, (rk, dil) in enumerate(zip(c.resblock_kernel_sizes, c.resblock_dilation_sizes)):
+                    rb = i * nk + j
+                    lastblock = j == nk - 1
+                    acc = Seq(B, T, cout, PHn, Tp, zero="edges")
+                    names = [f"resblocks.{rb}.convs1.{di}" for di in range(3)], [f"resblocks.{rb}.convs2.{di}" for di in range(3)]
+                    ops.hifigan_resblock(x_raw, [w[n + ".w"] for n in names[0]], [w[n + ".b"] for n in names[0]],
+                                         [w[n + ".w"] for n in names[1]], [w[n + ".b"] for n in names[1]], rk, list(dil),
+                                         res2=xs, gamma=(1.0 / nk) if lastblock else 1.0, out=acc,
+                                         out2=nxt_act if lastblock else None, out2_slope=last_slope)
+                    xs = acc
+                act = nxt_act
+                continue
+            x_act = Seq(B, T, cout, PHn, Tp, buf=up_act.buf.view(B * Tp, cout))
+            xs = None
             for j, (rk, dil) in enumerate(zip(c.resblock_kernel_sizes, c.resblock_dilation_sizes)):
                 rb = i * nk + j
                 y_raw, y_act = x_raw, x_act

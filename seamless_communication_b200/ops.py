@@ -110,6 +110,25 @@ def gemm_raw(a: torch.Tensor, w: torch.Tensor, n: int, bias=None, *, act=ACT_NON
     return out
 
 
+def hifigan_resblock(x: Seq, w1, b1, w2, b2, k: int, dil, *, res2: Optional[Seq] = None, gamma=1.0, out: Seq,
+                     out2: Optional[Seq] = None, out2_slope=0.0, slope=0.1) -> Seq:
+    """One fused HiFi-GAN ResBlock (hifigan.py:33-121) on a 16- or 32-channel Seq: out = (resblock(x) + res2) * gamma."""
+    lib = _lib.load()
+    assert len(dil) == 3 and len(w1) == len(w2) == len(b1) == len(b2) == 3
+    assert x.Tp == x.T + 2 * x.PH and x.buf.stride(0) == x.C
+    d = _lib.ResblockDesc()
+    d.x, d.res2, d.out, d.out2 = x.buf.data_ptr(), _p(None if res2 is None else res2.buf), out.buf.data_ptr(), _p(
+        None if out2 is None else out2.buf)
+    for i in range(3):
+        d.w1[i], d.b1[i], d.w2[i], d.b2[i] = w1[i].data_ptr(), b1[i].data_ptr(), w2[i].data_ptr(), b2[i].data_ptr()
+        d.dilation[i] = dil[i]
+    d.channels, d.kernel_size = x.C, k
+    d.batch, d.T, d.rows_per_seq, d.halo = x.B, x.T, x.Tp, x.PH
+    d.slope, d.gamma, d.out2_slope = slope, gamma, out2_slope
+    check(lib.sb_hifigan_resblock(C.byref(d), _stream()), "sb_hifigan_resblock")
+    return out
+
+
 def slice_rows(rows: int) -> int:
     """Row stride between split-K slices: padded to the GEMM tile height so the TMA-store epilogue applies."""
     return (rows + 127) // 128 * 128

@@ -388,6 +388,30 @@ def test_vocoder_matches_oracle_and_reference_golden(tiny):
         voc(units.to(dev), "xxx", -1, dur_prediction=False)
 
 
+def test_vocoder_fused_resblocks_match_conv_by_conv_path(tiny, ops):
+    """Stages with 16 / 32 channels run each ResBlock as one fused kernel (resblock.cu); the same stages conv by conv
+    through sb_gemm give the same waveform up to the fp16 rounding of one extra intermediate.  Lengths around the tile
+    size exercise first / interior / last tiles and the zeroed halos."""
+    vc, eng = tiny["vc"], tiny["voc"].code_generator
+    g = torch.Generator().manual_seed(8)
+    for U in (1, 7, 23):
+        units = torch.randint(0, vc.num_embeddings, (3, U), generator=g).to(dev)
+        assert eng.fused_resblocks
+        n0 = ops.launch_count()
+        a = eng(units, [25] * 3, [45] * 3)
+        n_fused = ops.launch_count() - n0
+        eng.fused_resblocks = False
+        try:
+            n0 = ops.launch_count()
+            b = eng(units, [25] * 3, [45] * 3)
+            n_plain = ops.launch_count() - n0
+        finally:
+            eng.fused_resblocks = True
+        assert n_fused < n_plain  # the fused path really ran
+        assert a.shape == b.shape == (3, 1, U * 320)
+        assert (a - b).abs().max() < 2e-3, (U, float((a - b).abs().max()))
+
+
 # ------------------------------------------------------------------------------------------------ boundary: Translator
 def test_translator_predict_s2st_and_s2tt(tiny):
     from seamless_communication_b200.inference import SequenceGeneratorOptions, Translator
