@@ -84,6 +84,13 @@ int sb_gemm(const sb_gemm_t* g, sb_stream_t stream);
  * products to rows [z*slice_rows, z*slice_rows + m) of `partials` (row stride n; slice_rows a multiple of 128 enables
  * the TMA-store epilogue).  Only a/w/shape fields of `g` are used. */
 int sb_gemm_splitk(const sb_gemm_t* g, int32_t splits, float* partials, int64_t slice_rows, sb_stream_t stream);
+/* The same products for at most 160 rows (one decoder step of 32 sentences x beam 5) on a short-latency kernel
+ * (cp.async + mma.sync, skinny_gemm.cu) instead of the TMA/tcgen05 pipeline, whose fixed set-up cost dominates at this
+ * size.  partials != NULL: split-K mode, same output contract as sb_gemm_splitk.  partials == NULL (splits must be 1):
+ * out = act(a . w^T + bias) in fp16, act in {none, relu}.  sb_gemm_skinny_supported returns 1 when the shape qualifies
+ * (taps 1, m <= 160, n % 64 == 0, c_in % (64 * splits) == 0, 16-byte aligned operands). */
+int sb_gemm_skinny_supported(const sb_gemm_t* g, int32_t splits);
+int sb_gemm_skinny(const sb_gemm_t* g, int32_t splits, float* partials, int64_t slice_rows, sb_stream_t stream);
 /* consumer of the partials: x += bias + sum_z partial[z] (x fp16 [rows][dim], updated in place) and h = LayerNorm(x).
  * Fuses the reduction into the LayerNorm that follows every residual GEMM of a pre-LN decoder layer
  * (StandardTransformerDecoderLayer, fairseq2.cpp:979-1060). */

@@ -88,6 +88,33 @@ def test_gemm_conv_mask_residual_dual_output(ops, taps, dil):
     assert full[1, o.PH + 33:].abs().max() == 0 and full[2].abs().max() == 0
 
 
+@pytest.mark.parametrize("rows,n,k,splits", [(160, 1024, 1024, 8), (160, 192, 128, 2), (37, 64, 512, 4), (1, 128, 64, 1),
+                                             (150, 256, 1024, 16)])
+def test_gemm_skinny_matches_simt_reference(ops, rows, n, k, splits):
+    """skinny_gemm.cu (cp.async + mma.sync, the decoder-step GEMM at <= 160 rows): split-K partials sum to the product,
+    and the direct mode applies bias + ReLU; both against the CUDA-core reference kernel."""
+    from seamless_communication_b200.ops import Seq
+    torch.manual_seed(rows + n)
+    a = Seq(1, rows, k, buf=torch.randn(rows, k, device=dev).half())
+    w = (torch.randn(n, k, device=dev) / math.sqrt(k)).half()
+    bias = torch.randn(n, device=dev)
+    want = ops.gemm_raw(a.buf, w, n, bias, act=ops.ACT_RELU, out_f32=True, ref=True)
+    SR = ops.slice_rows(rows)
+    part = torch.full((splits * SR, n), float("nan"), device=dev)
+    ops.gemm_splitk(a, w, n, splits, part, skinny=True)
+    got = part.view(splits, SR, n)[:, :rows].sum(0) + bias
+    assert torch.isnan(part.view(splits, SR, n)[:, rows:]).all()  # rows past `rows` are never written
+    assert (torch.relu(got) - want).abs().max() < 2e-3
+    out = Seq(1, rows, n)
+    out.buf.fill_(float("nan"))
+    ops.gemm_skinny(a, w, n, bias, act=ops.ACT_RELU, out=out)
+    assert (out.buf.float() - want).abs().max() < 4e-3  # + fp16 rounding of the output
+    # same partials as the tcgen05 split-K kernel up to fp32 summation order
+    part2 = torch.zeros((splits * SR, n), device=dev)
+    ops.gemm_splitk(a, w, n, splits, part2)
+    assert (part2.view(splits, SR, n)[:, :rows].sum(0) + bias - got).abs().max() < 1e-3
+
+
 @pytest.mark.parametrize("taps,Cc", [(3, 16), (7, 16), (11, 32), (11, 8)])
 def test_gemm_narrow_channel_conv(ops, taps, Cc):
     """C < 64 with dilation 1 takes the overlapping-row (K-collapsed) tensor-map path."""
@@ -187,10 +214,12 @@ def test_layernorm_attention_dwconv(ops):
     xc.buf.copy_(torch.randn(90, 256, device=dev).half())
     wd = (torch.randn(256, 31, device=dev) * 0.2).half()
     lw, lb = torch.randn(256, device=dev), torch.randn(256, device=dev)
-    yd = ops.dwconv_ln_silu(xc, wd, lw, lb, 31)
-    c = F.conv1d(F.pad(xc.buf.float().view(2, 45, 256).transpose(1, 2), (30, 0)), wd.float().view(256, 1, 31), groups=256)
-    ref = F.silu(F.layer_norm(c.transpose(1, 2), (256,), lw, lb, 1e-5)).reshape(90, 256)
-    assert rel(yd.buf, ref) < 2e-3
+    for kk in (31, 15):  # 31: register-resident fixed-size kernel (w2v-BERT 2.0); other sizes: generic kernel
+        wk = wd[:, :kk].contiguous()
+        yd = ops.dwconv_ln_silu(xc, wk, lw, lb, kk)
+        c = F.conv1d(F.pad(xc.buf.float().view(2, 45, 256).transpose(1, 2), (kk - 1, 0)), wk.float().view(256, 1, kk), groups=256)
+        ref = F.silu(F.layer_norm(c.transpose(1, 2), (256,), lw, lb, 1e-5)).reshape(90, 256)
+        assert rel(yd.buf, ref) < 2e-3
 
 
 def test_logits_topk_exact(ops):
