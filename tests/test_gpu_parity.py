@@ -369,6 +369,25 @@ def test_beam_search_ragged_encoder_and_early_eos(tiny):
 
 
 # ------------------------------------------------------------------------------------------------ T2U (a11-a14)
+def test_text_to_chars_matches_reference_fixture(tiny):
+    """sb_text_to_chars (per-token tables) against char sequences / lengths produced by the reference's own
+    NARDecoderFrontend.text_to_char_seqs (tests/golden/nar_frontend.npz): punctuation merge rules, unk, pad, bare space."""
+    from seamless_communication_b200.ops import Seq
+    cfg, eng = tiny["cfg"], tiny["model"].engine
+    d = np.load(os.path.join(G, "nar_frontend.npz"))
+    ts = torch.from_numpy(d["text_seqs"]).to(dev)
+    B, L = ts.shape
+    dec = Seq(B, L, cfg.model_dim, buf=(torch.randn(B * L, cfg.model_dim, device=dev) * 0.5).half(),
+              lens=torch.tensor([L, 7, 6], dtype=torch.int32, device=dev))
+    _, _, aux = eng.t2u(dec, ts)
+    assert np.array_equal(aux["char_lens"].cpu().numpy(), d["char_lens"])
+    assert np.array_equal(aux["char_seq_lens"].cpu().numpy(), d["char_seq_lens"])
+    got = aux["char_seqs"].cpu().numpy()
+    for b in range(B):
+        m = int(d["char_seq_lens"][b])
+        assert np.array_equal(got[b, :m], d["char_seqs"][b, :m])
+
+
 def test_t2u_matches_oracle(tiny):
     from seamless_communication_b200.ops import Seq
     cfg, uo, eng = tiny["cfg"], tiny["uo"], tiny["model"].engine

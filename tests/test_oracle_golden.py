@@ -53,3 +53,63 @@ def test_unit_token_decoder_nar():
     units[units == 1] = 5
     units -= 4
     assert np.array_equal(units.numpy(), d["nar_multilingual_v2.dec_out"])
+
+
+# ---- module-level fixtures: the reference's own in-tree modules, run by tests/golden/make_golden_modules.py ------------
+def _sd(d):
+    return {k[3:]: torch.from_numpy(d[k]) for k in d.files if k.startswith("sd/")}
+
+
+def test_pchoose_matches_reference_layer():
+    """models/monotonic_decoder/p_choose.py PChooseLayer (energy MLPs, ceil-mode key pooling, bias, temperature)."""
+    d = np.load(os.path.join(G, "pchoose.npz"))
+    o = UnityOracle(dict(model_dim=32, num_heads=4, max_seq_len=16), _sd(d))
+    p = o.p_choose(0, torch.from_numpy(d["seqs"]), torch.from_numpy(d["keys"]), temperature=0.2, ratio=2, n_energy=4)
+    assert p.shape == d["p_choose"].shape
+    assert np.abs(p.numpy() - d["p_choose"]).max() < 1e-5
+
+
+def test_fft_decoder_matches_reference_modules():
+    """models/unity/fft_decoder{,_layer}.py: post-LN FFT blocks, Conv1dBlock masking, final LayerNorm."""
+    d = np.load(os.path.join(G, "fft_decoder.npz"))
+    o = UnityOracle(dict(model_dim=32, num_heads=4, max_seq_len=16, t2u_dec_layers=2, fft_kernel=7), _sd(d))
+    x, lens = torch.from_numpy(d["x"]), torch.from_numpy(d["lens"])
+    km = torch.arange(x.shape[1])[None] < lens[:, None]
+    y = o.fft_decoder(x, km)
+    for b in range(x.shape[0]):  # rows past a sequence's length are don't-care (both sides compute them, nobody reads them)
+        n = int(lens[b])
+        assert np.abs(y[b, :n].numpy() - d["y"][b, :n]).max() < 2e-5
+
+
+def test_adaptor_layer_matches_reference_module():
+    """models/unity/adaptor_block.py UnitYTransformerAdaptorLayer: k8/s8/p4 pooling convs + GLU on both branches,
+    new padding mask (:426-438), attention + residual, pre-LN FFN."""
+    d = np.load(os.path.join(G, "adaptor_layer.npz"))
+    o = UnityOracle(dict(model_dim=32, num_heads=4, max_seq_len=16, adaptor_kernel=8, adaptor_stride=8), _sd(d))
+    y, lens = o.adaptor_layer(torch.from_numpy(d["x"]), torch.from_numpy(d["lens"]))
+    assert np.array_equal(lens.numpy(), d["out_lens"])
+    assert y.shape == d["y"].shape
+    for b in range(y.shape[0]):
+        n = int(lens[b])
+        assert np.abs(y[b, :n].numpy() - d["y"][b, :n]).max() < 2e-5
+
+
+def test_nar_frontend_matches_reference_module():
+    """models/unity/nar_decoder_frontend.py NARDecoderFrontend.forward on the tiny synthetic model: TagManager, the
+    punctuation / space merge rules of count_character_length_in_subword, char sequences, character-level upsampling,
+    VarianceAdaptor durations (two duration factors) and unit-level position embedding."""
+    d = np.load(os.path.join(G, "nar_frontend.npz"))
+    cfg = C.tiny_v2()
+    o = UnityOracle(cfg.to_dict(), S.make_unity_state_dict(cfg, seed=0), S.make_tokenizers(cfg))
+    ts, enc = torch.from_numpy(d["text_seqs"]), torch.from_numpy(d["enc"])
+    cs, csl, cl = o.text_to_char_seqs(ts)
+    assert np.array_equal(cs.numpy(), d["char_seqs"]) and np.array_equal(csl.numpy(), d["char_seq_lens"])
+    assert np.array_equal(cl.numpy(), d["char_lens"])
+    # ',' absorbs the space of the piece after it (2, then 5 - 1 = 4); '.' before a bare space piece does not (1)
+    assert d["char_lens"][0].tolist()[:6] == [0, 5, 2, 4, 2, 1]
+    for tag, factor in (("", 1.0), ("_f17", 1.7)):
+        x, ulens, dur, _ = o.nar_frontend(enc, ts, duration_factor=factor)
+        assert np.array_equal(dur.numpy(), d["durations" + tag]) and np.array_equal(ulens.numpy(), d["unit_lens" + tag])
+        for b in range(x.shape[0]):
+            n = int(ulens[b])
+            assert np.abs(x[b, :n].numpy() - d["seqs" + tag][b, :n]).max() < 1e-5
