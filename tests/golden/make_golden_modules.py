@@ -5,14 +5,15 @@
 
 Executed from /root/reference/src/seamless_communication (imported, nothing copied):
   * models/monotonic_decoder/p_choose.py       PChooseLayer.forward                          -> pchoose.npz
+  * models/monotonic_decoder/monotonic_decoder{,_layer}.py  MonotonicTransformerDecoder.forward -> monotonic_decoder.npz
   * models/unity/fft_decoder{,_layer}.py       FeedForwardTransformer (Conv1dBlock, post-LN) -> fft_decoder.npz
   * models/unity/adaptor_block.py              UnitYTransformerAdaptorLayer.forward          -> adaptor_layer.npz
   * models/unity/nar_decoder_frontend.py       NARDecoderFrontend.forward (TagManager, char-length rules, char
     + length_regulator.py                      sequences, hard upsampling, VarianceAdaptor)  -> nar_frontend.npz
 
 fairseq2 is absent offline.  The in-tree modules receive their fairseq2 collaborators as constructor arguments, so
-this script passes stand-ins for exactly three of them - a plain multi-head attention, a plain feed-forward network
-and a sinusoidal position encoder (the latter from oracle/unity_oracle.py: recalled, see oracle/ASSUMPTIONS.md #4).
+this script passes stand-ins for exactly four of them - a plain multi-head attention, a plain feed-forward network,
+a causal mask factory and a sinusoidal position encoder (the latter from oracle/unity_oracle.py: recalled, see oracle/ASSUMPTIONS.md #4).
 What the fixtures pin is therefore the arithmetic and control flow that live IN the reference tree: pooling convs,
 GLU, padding-mask arithmetic, residual / LayerNorm order, Conv1d blocks and their masking, the monotonic energy,
 the subword -> character bookkeeping and the duration / upsampling pipeline.  Parameter names come from the reference
@@ -51,6 +52,8 @@ class StdMultiheadAttention(torch.nn.Module):
         k = self.k_proj(keys).view(N, -1, H, K).transpose(1, 2)
         v = self.v_proj(values).view(N, -1, H, K).transpose(1, 2)
         w = torch.matmul(q, k.transpose(2, 3)) * K ** -0.5
+        if attn_mask is not None:
+            w = w + attn_mask.materialize()
         if key_padding_mask is not None:
             w = w.masked_fill(~key_padding_mask.materialize()[:, None, None, :], float("-inf"))
         o = torch.matmul(torch.softmax(w, dim=-1), v).transpose(1, 2).reshape(N, S, M)
@@ -101,13 +104,20 @@ def install_module_shims():
     class PositionEncoder(torch.nn.Module):
         pass
 
+    class CausalAttentionMaskFactory:
+        def __call__(self, seqs, keys, training=False, state_bag=None):
+            S = seqs.size(1)
+            m = torch.full((S, S), float("-inf")).triu(1)
+            return types.SimpleNamespace(materialize=lambda: m)
+
     placeholder = type("Placeholder", (), {})
     mod("overrides", final=identity)
     mod("fairseq2.typing", finaloverride=identity)
     mod("fairseq2.nn.module_list", ModuleList=ModuleList)
     mod("fairseq2.nn.transformer", MultiheadAttention=StdMultiheadAttention, AttentionMask=placeholder,
         FeedForwardNetwork=StdFeedForwardNetwork, LayerNormFactory=placeholder, TransformerEncoder=placeholder,
-        TransformerEncoderLayer=TransformerEncoderLayer, TransformerNormOrder=TransformerNormOrder)
+        TransformerEncoderLayer=TransformerEncoderLayer, TransformerNormOrder=TransformerNormOrder,
+        AttentionMaskFactory=placeholder, CausalAttentionMaskFactory=CausalAttentionMaskFactory)
     mod("fairseq2.models")
     mod("fairseq2.models.conformer", ConformerBlock=placeholder)
     mod("fairseq2.models.nllb")
@@ -146,6 +156,21 @@ def main():
         p = layer(seqs, keys)
     save("pchoose.npz", dict(seqs=seqs, keys=keys, p_choose=p, **{"sd/" + k: v for k, v in named_state(
         "text_decoder.layers.0.p_choose_layer", layer).items()}))
+
+    # ---- 1b. MonotonicTransformerDecoder: 2 layers around the real PChooseLayer (monotonic_decoder.py:21-98,
+    #          monotonic_decoder_layer.py:25-201) ------------------------------------------------------------
+    ml = importlib.import_module("seamless_communication.models.monotonic_decoder.monotonic_decoder_layer")
+    md = importlib.import_module("seamless_communication.models.monotonic_decoder.monotonic_decoder")
+    torch.manual_seed(25)
+    mlayers = [ml.MonotonicTransformerDecoderLayer(StdMultiheadAttention(32, 4), StdMultiheadAttention(32, 4),
+                                                   pc.PChooseLayer(32, 4, -0.5, 0.2, 4, 2), StdFeedForwardNetwork(32, 64),
+                                                   dropout_p=0.0) for _ in range(2)]
+    mdec = md.MonotonicTransformerDecoder(mlayers).eval()
+    x, enc = torch.randn(1, 6, 32), torch.randn(1, 9, 32)
+    with torch.inference_mode():
+        y, _, pch = mdec(x, None, enc, None)
+    save("monotonic_decoder.npz", dict(x=x, enc=enc, y=y, p_choose=pch,
+                                       **{"sd/" + k: v for k, v in named_state("text_decoder", mdec).items()}))
 
     # ---- 2. FeedForwardTransformer (fft_decoder.py:21-77, fft_decoder_layer.py:20-231) ---------------------
     fl = importlib.import_module("seamless_communication.models.unity.fft_decoder_layer")

@@ -1,4 +1,5 @@
-"""Pins the CPU oracle against vectors produced by the reference's own code (tests/golden/make_golden.py)."""
+"""Pins the CPU oracle against vectors produced by the reference's own code (tests/golden/make_golden.py and
+tests/golden/make_golden_modules.py)."""
 import os
 
 import numpy as np
@@ -67,6 +68,16 @@ def test_pchoose_matches_reference_layer():
     p = o.p_choose(0, torch.from_numpy(d["seqs"]), torch.from_numpy(d["keys"]), temperature=0.2, ratio=2, n_energy=4)
     assert p.shape == d["p_choose"].shape
     assert np.abs(p.numpy() - d["p_choose"]).max() < 1e-5
+
+
+def test_monotonic_decoder_matches_reference_modules():
+    """models/monotonic_decoder/{monotonic_decoder,monotonic_decoder_layer}.py: pre-LN layer order, p_choose taken from
+    the normalised cross-attention input, cat + flatten of the per-layer p_choose (:93-96)."""
+    d = np.load(os.path.join(G, "monotonic_decoder.npz"))
+    o = UnityOracle(dict(model_dim=32, num_heads=4, max_seq_len=16, dec_layers=2), _sd(d))
+    y, pc = o.monotonic_decoder_layers(torch.from_numpy(d["x"]), torch.from_numpy(d["enc"]))
+    assert np.abs(y.numpy() - d["y"]).max() < 2e-5
+    assert np.abs(pc.reshape(d["p_choose"].shape).numpy() - d["p_choose"]).max() < 1e-5
 
 
 def test_fft_decoder_matches_reference_modules():
