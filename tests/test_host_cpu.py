@@ -40,6 +40,36 @@ def test_no_cpu_fallback():
         _lib.require_cuda()
 
 
+def test_product_package_never_touches_the_oracle_or_the_reference_tree():
+    """The oracle is test infrastructure: only tests/, __graft_entry__.smoke() and bench.py's CPU legs may import it.
+    No module of the product package may import `oracle`, shell out to it, or read /root/reference at run time."""
+    pkg = os.path.join(ROOT, "seamless_communication_b200")
+    offenders = []
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if not f.endswith((".py", ".cu", ".cuh", ".h")):
+                continue
+            src = open(os.path.join(dirpath, f), encoding="utf-8").read()
+            if re.search(r"^\s*(from|import)\s+oracle\b", src, re.M) or "oracle/_ref" in src or "libknf_ref" in src \
+                    or re.search(r"[\"']/root/reference", src):
+                offenders.append(os.path.relpath(os.path.join(dirpath, f), ROOT))
+    assert not offenders, offenders
+    # and the struct layouts the ctypes binding declares match the header's field lists (same names, same order)
+    hdr = open(os.path.join(ROOT, "include", "seamless_b200.h")).read()
+    for ctype, cname in ((_lib.GemmDesc, "sb_gemm_t"), (_lib.BeamDesc, "sb_beam_t"), (_lib.ResblockDesc, "sb_resblock_t")):
+        body = re.search(r"typedef struct \{([^{}]*)\}\s*" + cname + ";", hdr, re.S).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        names = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            first, *rest = decl.split(",")
+            names.append(re.findall(r"(\w+)\s*(?:\[\d+\])?$", first.strip())[0])
+            names += [re.findall(r"(\w+)\s*(?:\[\d+\])?$", r.strip())[0] for r in rest]
+        assert names == [f[0] for f in ctype._fields_], (cname, names, [f[0] for f in ctype._fields_])
+
+
 def test_unit_tokenizer_matches_reference_kats():
     d = np.load(os.path.join(G, "unit_tokenizer.npz"))
     langs = ["eng", "deu", "fra"]
