@@ -8,6 +8,7 @@ Executed from /root/reference/src/seamless_communication (imported, nothing copi
   * models/monotonic_decoder/monotonic_decoder{,_layer}.py  MonotonicTransformerDecoder.forward -> monotonic_decoder.npz
   * models/unity/fft_decoder{,_layer}.py       FeedForwardTransformer (Conv1dBlock, post-LN) -> fft_decoder.npz
   * models/unity/adaptor_block.py              UnitYTransformerAdaptorLayer.forward          -> adaptor_layer.npz
+                                               UnitYEncoderAdaptor.forward                   -> encoder_adaptor.npz
   * models/unity/nar_decoder_frontend.py       NARDecoderFrontend.forward (TagManager, char-length rules, char
     + length_regulator.py                      sequences, hard upsampling, VarianceAdaptor)  -> nar_frontend.npz
 
@@ -115,7 +116,7 @@ def install_module_shims():
     mod("fairseq2.typing", finaloverride=identity)
     mod("fairseq2.nn.module_list", ModuleList=ModuleList)
     mod("fairseq2.nn.transformer", MultiheadAttention=StdMultiheadAttention, AttentionMask=placeholder,
-        FeedForwardNetwork=StdFeedForwardNetwork, LayerNormFactory=placeholder, TransformerEncoder=placeholder,
+        FeedForwardNetwork=StdFeedForwardNetwork, LayerNormFactory=placeholder, TransformerEncoder=TransformerEncoderLayer,
         TransformerEncoderLayer=TransformerEncoderLayer, TransformerNormOrder=TransformerNormOrder,
         AttentionMaskFactory=placeholder, CausalAttentionMaskFactory=CausalAttentionMaskFactory)
     mod("fairseq2.models")
@@ -194,6 +195,23 @@ def main():
         y, pm = ad(x, PaddingMask(lens, 43))
     save("adaptor_layer.npz", dict(x=x, lens=lens, y=y, out_lens=pm.seq_lens,
                                    **{"sd/" + k: v for k, v in named_state("speech_encoder.adaptor_layers.0", ad).items()}))
+
+    # ---- 3b. UnitYEncoderAdaptor around an identity inner encoder (adaptor_block.py:30-125) ------------------
+    class IdentityEncoder(torch.nn.Module):
+        model_dim = 32
+
+        def forward(self, seqs, padding_mask):
+            return seqs, padding_mask
+
+    torch.manual_seed(26)
+    ea = ab.UnitYEncoderAdaptor(IdentityEncoder(), [ab.UnitYTransformerAdaptorLayer(
+        StdMultiheadAttention(32, 4), StdFeedForwardNetwork(32, 64), kernel_size=8, stride=8, dropout_p=0.0)],
+        inner_layer_norm=True).eval()
+    x, lens = torch.randn(2, 29, 32), torch.tensor([29, 17])
+    with torch.inference_mode():
+        y, pm = ea(x, PaddingMask(lens, 29))
+    save("encoder_adaptor.npz", dict(x=x, lens=lens, y=y, out_lens=pm.seq_lens,
+                                     **{"sd/" + k: v for k, v in named_state("speech_encoder", ea).items()}))
 
     # ---- 4. NARDecoderFrontend on the tiny synthetic model (nar_decoder_frontend.py:52-334) -----------------
     nf = importlib.import_module("seamless_communication.models.unity.nar_decoder_frontend")

@@ -105,6 +105,18 @@ def test_adaptor_layer_matches_reference_module():
         assert np.abs(y[b, :n].numpy() - d["y"][b, :n]).max() < 2e-5
 
 
+def test_encoder_adaptor_matches_reference_module():
+    """models/unity/adaptor_block.py UnitYEncoderAdaptor: inner LayerNorm, x + 0.5 * proj2(relu(proj1 x)), adaptor
+    layers, final LayerNorm."""
+    d = np.load(os.path.join(G, "encoder_adaptor.npz"))
+    o = UnityOracle(dict(model_dim=32, num_heads=4, max_seq_len=16, adaptor_kernel=8, adaptor_stride=8), _sd(d))
+    y, lens = o.encoder_adaptor(torch.from_numpy(d["x"]), torch.from_numpy(d["lens"]))
+    assert np.array_equal(lens.numpy(), d["out_lens"])
+    for b in range(y.shape[0]):
+        n = int(lens[b])
+        assert np.abs(y[b, :n].numpy() - d["y"][b, :n]).max() < 2e-5
+
+
 def test_nar_frontend_matches_reference_module():
     """models/unity/nar_decoder_frontend.py NARDecoderFrontend.forward on the tiny synthetic model: TagManager, the
     punctuation / space merge rules of count_character_length_in_subword, char sequences, character-level upsampling,
