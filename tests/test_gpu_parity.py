@@ -543,7 +543,7 @@ def test_monotonic_decoder_pchoose_and_policy_match_oracle():
     assert rel(dec, o_dec) < 5e-3
     assert (pc.cpu() - o_pc).abs().max() < 2e-2                               # probabilities in (0,1), sigmoid(e/0.2)
     # streaming: the same READ/WRITE decisions chunk by chunk (prob compared with a margin around the threshold)
-    pol = MMATextDecoderPolicy(model, "spa", max_len_b=10)
+    pol = MMATextDecoderPolicy(model, "spa", max_len_a=0, max_len_b=10)
     written, o_target = [], []
     for n, fin in ((5, False), (9, False), (13, True)):
         new, finished = pol.policy(enc[:, :n].to(dev), fin)
@@ -551,4 +551,6 @@ def test_monotonic_decoder_pchoose_and_policy_match_oracle():
         o_target += o_new
         written += new
         assert new == o_new and finished == o_fin
+        if finished:
+            break
     assert written == o_target and len(written) > 0

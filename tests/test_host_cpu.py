@@ -70,6 +70,95 @@ def test_product_package_never_touches_the_oracle_or_the_reference_tree():
         assert names == [f[0] for f in ctype._fields_], (cname, names, [f[0] for f in ctype._fields_])
 
 
+# ---- streaming policy (a17): pinned against the reference agent -------------------------------------------------------
+def _policy_script():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("policy_script", os.path.join(G, "policy_script.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+class _ScriptedModel:
+    """decode / project of the monotonic decoder replaced by the deterministic script the fixture generator used."""
+
+    def __init__(self, ps, salt):
+        self.ps, self.salt = ps, salt
+
+    def decode(self, ids, encoder_output):
+        row = ids[0].tolist()
+        logits, probs = self.ps.script(row, int(encoder_output.shape[1]), self.salt)
+        dec = torch.zeros(1, len(row), self.ps.VOCAB)
+        dec[0, -1] = torch.from_numpy(logits)
+        pc = torch.full((self.ps.LAYERS, self.ps.HEADS, len(row), 4), 0.5)
+        pc[:, :, -1, -1] = torch.from_numpy(probs)
+        return dec, pc
+
+    def project(self, dec):
+        return dec
+
+
+def test_streaming_policy_matches_reference_agent_traces():
+    """MMATextDecoderPolicy against call-by-call traces of the reference's MMATextDecoderAgent.policy
+    (tests/golden/policy_traces.json, made by tests/golden/make_golden_policy.py): thresholds and decision methods,
+    length budget incl. the double-count re-check, burst limit, starting wait, no_early_stop, both n-gram rules."""
+    import json
+    from seamless_communication_b200.streaming import MMATextDecoderPolicy
+    ps = _policy_script()
+    traces = json.load(open(os.path.join(G, "policy_traces.json")))
+    assert set(traces) == {s["name"] for s in ps.SCENARIOS}
+    assert sum(t["ngram_blocks"] for t in traces.values()) >= 20  # the repeat rules are really exercised
+    for name, tr in traces.items():
+        a = tr["args"]
+        pol = MMATextDecoderPolicy(_ScriptedModel(ps, tr["salt"]), prefix=[ps.EOS, 5], eos_idx=ps.EOS,
+                                   decision_threshold=a["decision_threshold"], decision_method=a["decision_method"],
+                                   p_choose_start_layer=a["p_choose_start_layer"], max_len_a=a["max_len_a"],
+                                   max_len_b=a["max_len_b"], max_consecutive_writes=a["max_consecutive_write"],
+                                   min_starting_wait=a["min_starting_wait"], no_early_stop=a["no_early_stop"],
+                                   block_ngrams=a["block_ngrams"])
+        for i, call in enumerate(tr["calls"]):
+            new, finished = pol.policy(torch.zeros(1, call["src"], 8), call["final"])
+            if call["action"] == "R":
+                assert (new, finished) == ([], False), (name, i, new, finished)
+            else:
+                assert new == call["tokens"] and finished == call["finished"], (name, i, new, call)
+        assert pol.target_finished == tr["calls"][-1].get("finished", False), name
+
+
+def test_streaming_policy_agrees_with_oracle_policy_on_the_oracle_model():
+    """The flow of tests/test_gpu_parity.py::test_monotonic_decoder_pchoose_and_policy_match_oracle with the CUDA model
+    replaced by the fp32 oracle: product policy and oracle policy take the same decisions given the same model."""
+    from oracle.unity_oracle import UnityOracle
+    from seamless_communication_b200.streaming import MMATextDecoderPolicy
+    cfg = C.tiny_v2()
+    sd = S.make_monotonic_state_dict(cfg, seed=2)
+    toks = S.make_tokenizers(cfg)
+    uo = UnityOracle(cfg.to_dict(), sd, toks)
+
+    class OracleModel:
+        def decode(self, ids, enc):
+            return uo.monotonic_decoder(ids, enc)
+
+        def project(self, dec):
+            return uo.project(dec)
+
+    torch.manual_seed(4)
+    enc = torch.randn(1, 13, cfg.model_dim).half().float()
+    prefix = [3, toks[0].lang_index("spa")]
+    for budget in (10, 3):
+        pol = MMATextDecoderPolicy(OracleModel(), prefix=prefix, eos_idx=cfg.text_eos, max_len_a=0, max_len_b=budget)
+        written, o_target = [], []
+        for n, fin in ((5, False), (9, False), (13, True)):
+            new, finished = pol.policy(enc[:, :n], fin)
+            o_new, o_fin = uo.emma_policy(enc[:, :n], prefix, o_target, fin, max_len=budget)
+            o_target += o_new
+            written += new
+            assert new == o_new and finished == o_fin, (budget, n, new, o_new, finished, o_fin)
+            if finished:
+                break
+        assert written == o_target and len(written) > 0
+
+
 def test_unit_tokenizer_matches_reference_kats():
     d = np.load(os.path.join(G, "unit_tokenizer.npz"))
     langs = ["eng", "deu", "fra"]
