@@ -163,5 +163,39 @@ def main():
     json.dump(traces, open(os.path.join(HERE, "policy_traces.json"), "w"), indent=1)
 
 
+
+
+def ngram_filter_fixture():
+    """remove_consecutive_repeated_ngrams (inference/generator.py:39-56): the function is lifted out of the reference file
+    with ast (the module itself needs fairseq2) and executed on seeded random sequences -> ngram_filter.json."""
+    import ast
+    import random
+    from typing import List  # noqa: F401  (used by the extracted signature)
+
+    path = os.path.join(REF, "src", "seamless_communication", "inference", "generator.py")
+    tree = ast.parse(open(path).read())
+    fn = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "remove_consecutive_repeated_ngrams")
+    ns = {"List": List}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), path, "exec"), ns)
+    ref = ns["remove_consecutive_repeated_ngrams"]
+    rng = random.Random(5)
+    cases = []
+    for i in range(200):
+        n = rng.randint(0, 60)
+        alphabet = rng.choice([2, 3, 5, 50])
+        seq = [rng.randrange(alphabet) for _ in range(n)]
+        if i % 4 == 0 and n > 6:  # plant exact repeats of longer n-grams
+            k = rng.randint(2, min(12, n // 2))
+            s = rng.randint(0, n - 2 * k)
+            seq[s + k:s + 2 * k] = seq[s:s + k]
+        lo = rng.choice([1, 1, 2, 3])
+        hi = rng.choice([lo, 4, 40])
+        hi = max(hi, lo)
+        cases.append(dict(seq=seq, min_size=lo, max_size=hi, out=ref(list(seq), lo, hi)))
+    json.dump(cases, open(os.path.join(HERE, "ngram_filter.json"), "w"))
+    print("wrote ngram_filter.json", len(cases), "cases;", sum(c["out"] != c["seq"] for c in cases), "changed")
+
+
 if __name__ == "__main__":
     main()
+    ngram_filter_fixture()

@@ -181,6 +181,9 @@ def test_unit_tokenizer_matches_reference_kats():
 
 
 def test_ngram_filter_and_options_defaults():
+    import json
+    for c in json.load(open(os.path.join(G, "ngram_filter.json"))):  # outputs of the reference's own function
+        assert remove_consecutive_repeated_ngrams(list(c["seq"]), c["min_size"], c["max_size"]) == c["out"]
     assert remove_consecutive_repeated_ngrams([1, 2, 2, 3]) == [1, 2, 3]
     assert remove_consecutive_repeated_ngrams([1, 2, 3, 1, 2, 3, 4]) == [1, 2, 3, 4]
     assert remove_consecutive_repeated_ngrams([]) == []
