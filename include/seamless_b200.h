@@ -124,7 +124,7 @@ int sb_layernorm(const void* x, const void* res, void* y, void* sum_out, const f
 /* ------------------------------------------------------------------------------------------------------------------
  * sb_attention - multi-head scaled dot-product attention, head_dim 64, fp16 io, fp32 softmax, flash-style.
  *   scores = (q.k^T + q.rel_k[clamp(j-i,-left,right)+left]) / 8, key mask j < kv_lens[b], optional causal mask.
- * q/k/v/out pointers address row 0 of sequence 0 (sequence layout given by *_rows/*_halo), *_ld = row stride.
+ * q/k/v/out pointers address row 0 of sequence 0 (sequence layout given by the x_rows / x_halo arguments), x_ld = row stride.
  * Replaces MultiheadAttention_forward (fairseq2.cpp:399-499) and ShawRelativePositionSDPA
  * (models/conformer_shaw/builder.py:127-146).
  * ---------------------------------------------------------------------------------------------------------------- */

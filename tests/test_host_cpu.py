@@ -31,6 +31,20 @@ def test_library_exports_every_header_symbol():
     assert lib.sb_version() >= 1
 
 
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """The drop-in boundary is a C ABI: include/seamless_b200.h compiles as C99 and a C program links against the library."""
+    src = tmp_path / "t.c"
+    src.write_text('#include "seamless_b200.h"\n'
+                   "int main(void) { sb_gemm_t g; sb_resblock_t r; sb_beam_t b; (void)g; (void)r; (void)b;\n"
+                   "  return (sb_version() >= 1 && sb_launch_count() >= 0) ? 0 : 1; }\n")
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    exe = tmp_path / "t"
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src),
+                        "-o", str(exe), "-L", libdir, "-lseamless_b200", "-Wl,-rpath," + libdir], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert subprocess.run([str(exe)]).returncode == 0
+
+
 def test_no_cpu_fallback():
     if torch.cuda.is_available():
         pytest.skip("GPU present")
