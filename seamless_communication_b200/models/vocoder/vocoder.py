@@ -21,21 +21,23 @@ class Vocoder:
 
     def forward(self, units: Tensor, lang_list: Union[List[str], str], spkr_list: Union[Optional[List[int]], int] = None,
                 dur_prediction: bool = True) -> Tensor:
-        if len(units.shape) == 1:
-            units = units.unsqueeze(0)
-        if isinstance(lang_list, str):
-            lang_list = [lang_list] * units.size(0)
-        if isinstance(spkr_list, int):
-            spkr_list = [spkr_list] * units.size(0)
-        lang_idx_list = [self.lang_spkr_idx_map["multilingual"][l] for l in lang_list]
-        if not spkr_list:
-            spkr_list = [-1 for _ in range(len(lang_list))]
-        spkr_list = [self.lang_spkr_idx_map["multispkr"][lang_list[i]][0] if spkr_list[i] == -1 else spkr_list[i]
-                     for i in range(len(spkr_list))]
+        """Same argument conventions as the reference's Vocoder.forward (models/vocoder/vocoder.py:25-49): a single
+        language / speaker applies to the whole batch, speaker -1 (or None) selects the language's first speaker."""
+        if units.dim() == 1:
+            units = units[None]
+        n = units.size(0)
+        langs = [lang_list] * n if isinstance(lang_list, str) else list(lang_list)
+        if spkr_list is None or (not isinstance(spkr_list, int) and len(spkr_list) == 0):
+            spkrs = [-1] * len(langs)
+        else:
+            spkrs = [spkr_list] * n if isinstance(spkr_list, int) else list(spkr_list)
+        table = self.lang_spkr_idx_map
+        lang_ids = [table["multilingual"][name] for name in langs]
+        spkr_ids = [table["multispkr"][name][0] if s == -1 else s for name, s in zip(langs, spkrs)]
         if dur_prediction:
             # only the AR-T2U (v1) models need the vocoder's own duration predictor (translator.py:381-394)
             raise NotImplementedError("vocoder duration prediction belongs to the v1 AR T2U path (SURVEY 8f.4)")
-        return self.code_generator(units.view(units.size(0), -1), lang_idx_list, spkr_list)
+        return self.code_generator(units.reshape(n, -1), lang_ids, spkr_ids)
 
     __call__ = forward
 

@@ -196,6 +196,40 @@ def ngram_filter_fixture():
     print("wrote ngram_filter.json", len(cases), "cases;", sum(c["out"] != c["seq"] for c in cases), "changed")
 
 
+def vocoder_facade_fixture():
+    """Vocoder.forward argument handling (models/vocoder/vocoder.py:25-49: language / speaker broadcasting, -1 -> the
+    language's first speaker) executed from the reference with a recording code generator -> vocoder_facade.json."""
+    import importlib.util
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from seamless_communication_b200 import config as C
+    m = types.ModuleType("seamless_communication.models.vocoder.codehifigan")
+    m.CodeGenerator = object
+    sys.modules.setdefault("seamless_communication.models.vocoder", types.ModuleType("seamless_communication.models.vocoder"))
+    sys.modules["seamless_communication.models.vocoder.codehifigan"] = m
+    spec = importlib.util.spec_from_file_location(
+        "ref_vocoder", os.path.join(REF, "src", "seamless_communication", "models", "vocoder", "vocoder.py"))
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    seen = []
+
+    class Recorder(torch.nn.Module):
+        def forward(self, x, dur_prediction):
+            seen.append(dict(code_shape=list(x["code"].shape), spkr=x["spkr"].view(-1).tolist(), lang=x["lang"].view(-1).tolist(),
+                             dur_prediction=bool(dur_prediction)))
+            return torch.zeros(1)
+
+    voc = ref.Vocoder(Recorder(), C.vocoder_lang_spkr_idx_map())
+    calls = [dict(units_shape=[2, 5], lang="spa", spkr=-1), dict(units_shape=[5], lang=["fra"], spkr=None),
+             dict(units_shape=[2, 5], lang=["fra", "eng"], spkr=[3, -1]), dict(units_shape=[3, 4], lang="deu", spkr=7),
+             dict(units_shape=[2, 3], lang=["cmn", "hin"], spkr=[]), dict(units_shape=[1, 6], lang="eng", spkr=[-1])]
+    for c in calls:
+        voc(torch.zeros(c["units_shape"], dtype=torch.int64), c["lang"], c["spkr"], dur_prediction=False)
+        c["seen"] = seen[-1]
+    json.dump(calls, open(os.path.join(HERE, "vocoder_facade.json"), "w"), indent=1)
+    print("wrote vocoder_facade.json", [c["seen"]["spkr"] for c in calls])
+
+
 if __name__ == "__main__":
     main()
     ngram_filter_fixture()
+    vocoder_facade_fixture()

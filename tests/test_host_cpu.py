@@ -205,6 +205,23 @@ def test_ngram_filter_and_options_defaults():
     assert (o.beam_size, o.soft_max_seq_len, o.hard_max_seq_len, o.unk_penalty, o.len_penalty) == (5, (1, 200), 1024, 0.0, 1.0)
 
 
+def test_vocoder_facade_argument_handling_matches_reference():
+    """Vocoder.forward's language / speaker resolution against the reference's own Vocoder.forward
+    (tests/golden/vocoder_facade.json), with a recording stand-in for the CUDA engine."""
+    import json
+    from seamless_communication_b200.models.vocoder.vocoder import Vocoder
+    seen = []
+    voc = Vocoder(lambda units, lang, spkr: seen.append((list(units.shape), lang, spkr)), C.vocoder_lang_spkr_idx_map())
+    for c in json.load(open(os.path.join(G, "vocoder_facade.json"))):
+        voc(torch.zeros(c["units_shape"], dtype=torch.int64), c["lang"], c["spkr"], dur_prediction=False)
+        shape, lang, spkr = seen[-1]
+        assert shape == c["seen"]["code_shape"] and lang == c["seen"]["lang"] and spkr == c["seen"]["spkr"], c
+    with pytest.raises(KeyError):
+        voc(torch.zeros(2, 3, dtype=torch.int64), "xxx", -1, dur_prediction=False)
+    with pytest.raises(NotImplementedError):
+        voc(torch.zeros(2, 3, dtype=torch.int64), "eng", -1, dur_prediction=True)
+
+
 def test_task_routing_and_padding_mask():
     assert Translator.get_modalities_from_task_str("s2st") == (Modality.SPEECH, Modality.SPEECH)
     assert Translator.get_modalities_from_task_str("S2TT") == (Modality.SPEECH, Modality.TEXT)
