@@ -46,12 +46,15 @@ inline void count_launch(int n = 1) { g_launch_count += n; }
     sb::count_launch();                                                                  \
   } while (0)
 
-// Programmatic dependent launch (PDL): every kernel of the path triggers its dependents at entry and waits for its
-// prerequisites right before it first touches data produced upstream, so launch latency, prologues (barrier init,
-// TMEM allocation, descriptor fetch) and - in the GEMM - the weight loads of kernel N+1 overlap with kernel N.
+// Programmatic dependent launch (PDL, opt-in with SB_PDL=1): every kernel waits for its prerequisites right before it
+// first touches data produced upstream and only THEN lets its own dependents launch, so launch latency, prologues
+// (barrier init, TMEM allocation, descriptor fetch) and - in the GEMMs - the weight loads of kernel N+1 overlap with
+// kernel N, while at most one generation of dependents is resident.  (Round 1 triggered at kernel entry: the whole
+// chain then launches ahead, every waiting kernel pins shared memory / TMEM, and the step got slower - 425 vs 402 ms.)
 // Both instructions are no-ops when the kernel was launched without the attribute.
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_sync() { pdl_wait(); pdl_trigger(); }
 
 bool pdl_enabled();
 

@@ -17,8 +17,7 @@ __global__ void embed_kernel(const int* __restrict__ ids, long long ids_ld, cons
                              const elem_t* __restrict__ embed, const float* __restrict__ pos, float scale,
                              elem_t* __restrict__ x, int dim) {
   // grid: (rows, L); x row = r*L + t.  With step_ptr the single column `*step_ptr` is embedded at position *step_ptr.
-  pdl_trigger();
-  pdl_wait();
+  pdl_sync();
   const int r = blockIdx.x, t = blockIdx.y;
   const int id_col0 = step_ptr ? *step_ptr : 0, pos0 = id_col0;
   const int tok = ids[(long long)r * ids_ld + id_col0 + t];
@@ -140,8 +139,7 @@ __global__ void __launch_bounds__(128) decode_self_attn_kernel(const elem_t* __r
                                                                elem_t* __restrict__ out, int rows, int heads) {
   extern __shared__ float sc_all[];  // [4][max_len] scores + [4][max_len] ancestor slots
   __shared__ __align__(16) elem_t s_new[4][3][HD];
-  pdl_trigger();
-  pdl_wait();
+  pdl_sync();
   const int step = *step_ptr;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r = blockIdx.x;
@@ -188,8 +186,7 @@ __global__ void __launch_bounds__(128) decode_cross_attn_kernel(const elem_t* __
                                                                 elem_t* __restrict__ out, int rows, int beam, int heads) {
   extern __shared__ float sc_all[];  // [4][s_enc]
   __shared__ __align__(16) elem_t s_q[4][HD];
-  pdl_trigger();
-  pdl_wait();
+  pdl_sync();
   const int warp = threadIdx.x >> 5;
   const int r = blockIdx.x;
   const int h = blockIdx.y * 4 + warp;
@@ -231,8 +228,7 @@ __global__ void __launch_bounds__(TK_THREADS) logits_topk_kernel(const float* __
                                                                  int pad_idx, int eos_idx, int unk_idx, float unk_penalty, int K,
                                                                  float* __restrict__ cand_val, int* __restrict__ cand_idx,
                                                                  float* __restrict__ eos_lprob) {
-  pdl_trigger();
-  pdl_wait();
+  pdl_sync();
   const int r = blockIdx.x;
   const float* row = logits + (long long)r * ld;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -351,8 +347,7 @@ __global__ void __launch_bounds__(TK_THREADS) logits_topk_kernel(const float* __
 // ------------------------------------------------------------------------------------------- beam bookkeeping
 // one CTA per sentence; the step index is read from device memory so that one captured CUDA graph serves every step
 __global__ void __launch_bounds__(128) beam_step_kernel(const sb_beam_t p) {
-  pdl_trigger();
-  pdl_wait();
+  pdl_sync();
   const int b = blockIdx.x;
   const int beam = p.beam, K = p.K, ML = p.max_len;
   const int step = *p.step_ptr;
@@ -452,15 +447,13 @@ __global__ void __launch_bounds__(128) beam_step_kernel(const sb_beam_t p) {
 // hist[step][...] = h: keeps the final-LayerNorm decoder state of every search step so that the states of the winning
 // hypothesis can be gathered afterwards instead of re-running the decoder teacher-forced (inference/generator.py:294-299)
 __global__ void store_step_kernel(const uint4* __restrict__ h, uint4* __restrict__ hist, const int* __restrict__ step_ptr, long long n16) {
-  pdl_trigger();
-  pdl_wait();
+  pdl_sync();
   uint4* dst = hist + (long long)(*step_ptr) * n16;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (long long)gridDim.x * blockDim.x) dst[i] = h[i];
 }
 
 __global__ void step_advance_kernel(int* step_ptr) {
-  pdl_trigger();
-  pdl_wait();
+  pdl_sync();
   *step_ptr += 1;
 }
 

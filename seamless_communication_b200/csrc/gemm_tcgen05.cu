@@ -185,7 +185,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint32_t* tmem_ptr_smem = (uint32_t*)(tmem_full_bar + 1);
   float* bias_s = (float*)(smem + STAGES * Cfg::STAGE_BYTES + 256);
 
-  pdl_trigger();
   if (threadIdx.x == 0) {
     TL(0);
     // hide the descriptor fetch of the first TMA behind the barrier / TMEM setup
@@ -287,7 +286,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // ------------------------------------------------------------------ epilogue (warps 0..3)
-    pdl_wait();  // residual reads / output writes below must not overtake the upstream kernel
+    pdl_sync();  // residual reads / output writes below must not overtake the upstream kernel; dependents may launch now
     if (warp == 0 && g.prefetch_bytes > 0) {
       // latency-bound chains (decoder step): the next GEMM's weights do not depend on this kernel's result, so each CTA
       // asks L2 for its share now; the next kernel's first TMA loads then hit L2 instead of paying an HBM round trip

@@ -11,8 +11,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const elem_t* __restrict
                                                         const float* __restrict__ w, const float* __restrict__ bvec, int dim,
                                                         long long total_rows, int T, int in_rows, int in_halo, int out_rows,
                                                         int out_halo, const int* __restrict__ lens, int mask_out) {
-  pdl_trigger();
-  pdl_wait();
+  pdl_sync();
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= total_rows) return;
@@ -106,13 +105,12 @@ __global__ void __launch_bounds__(32 * LN_MAX_CHUNKS) splitk_reduce_ln_kernel(co
                                                                               const float* __restrict__ bias, elem_t* __restrict__ x,
                                                                               const float* __restrict__ w,
                                                                               const float* __restrict__ bvec, elem_t* __restrict__ h) {
-  pdl_trigger();
   __shared__ float s_part[2][LN_MAX_CHUNKS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   const long long row = blockIdx.x;
   const int off = warp * 256 + lane * 8;
   const bool act = off < dim;
-  pdl_wait();
+  pdl_sync();
   float v[8];
   float s = 0.f;
   if (act) {

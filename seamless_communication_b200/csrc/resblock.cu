@@ -150,14 +150,13 @@ __global__ void __launch_bounds__(RB_THREADS, C == 16 ? 2 : 1) resblock_kernel(c
   elem_t* as = xs + Cfg::BUF;                        // lrelu(x)
   elem_t* ts = as + Cfg::BUF;                        // lrelu(convs1(lrelu(x)))
   elem_t* ws = ts + Cfg::BUF;                        // weights of the conv in flight
-  pdl_trigger();
   const int hk = (p.k - 1) >> 1;
   const int H = hk * (p.dil[0] + p.dil[1] + p.dil[2] + 3);  // receptive-field half width of the whole ResBlock
   const int TT = RB_ROWS - 2 * H;                            // valid outputs per tile
   const int b = blockIdx.y;
   const int t_first = blockIdx.x * TT - H;                   // time index of tile row 0
   const long long seq0 = ((long long)b * p.Tp + p.PH) * C;   // element offset of (b, t = 0)
-  pdl_wait();
+  pdl_sync();
   // guard rows (never part of a valid output's receptive field, zeroed so that no NaN pattern is ever multiplied)
   for (int i = threadIdx.x; i < RB_GUARD * LD / 8 * 2; i += RB_THREADS) {
     const int side = i / (RB_GUARD * LD / 8), j = i - side * (RB_GUARD * LD / 8);

@@ -69,7 +69,6 @@ __global__ void __launch_bounds__(SK_THREADS, 2) skinny_gemm_kernel(const Skinny
   const int n0 = blockIdx.x * SK_BN;
   const int k_begin = blockIdx.y * p.k_per_split;
   const int chunks = p.k_per_split / SK_KCH;
-  pdl_trigger();
 
   // stage loader: A rows [0, 160) (rows >= p.rows zero-filled) then the W rows of this n-tile, 8 x 16 B per row
   auto load_stage = [&](int chunk, int stage) {
@@ -85,8 +84,8 @@ __global__ void __launch_bounds__(SK_THREADS, 2) skinny_gemm_kernel(const Skinny
       }
     }
   };
-  // weights do not depend on the upstream kernel; activations do (griddepcontrol.wait is a no-op without PDL)
-  pdl_wait();
+  // a stage mixes weights with activations of the upstream kernel, so the wait precedes the first copy
+  pdl_sync();
 #pragma unroll
   for (int s = 0; s < SK_STAGES - 1; ++s) {
     if (s < chunks) load_stage(s, s);
