@@ -136,3 +136,55 @@ def test_nar_frontend_matches_reference_module():
         for b in range(x.shape[0]):
             n = int(ulens[b])
             assert np.abs(x[b, :n].numpy() - d["seqs" + tag][b, :n]).max() < 1e-5
+
+
+# ---- the reference's own C++ restatement of fairseq2, compiled in place (oracle/Makefile) and driven by
+# ---- tests/golden/make_golden_beam.py ------------------------------------------------------------------------------------
+def _beam_model():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("beam_model", os.path.join(G, "beam_model.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_decoder_logits_match_reference_cpp():
+    """Embedding frontend (scaled embedding + positional table), pre-LN decoder layers (self-attention with causal mask,
+    encoder-decoder attention, ReLU FFN), final LayerNorm and tied projection against StandardTransformerDecoder_forward /
+    Linear_forward of ggml/examples/unity/fairseq2.cpp.  Tolerance: ggml evaluates exp() through an fp16 table."""
+    BM = _beam_model()
+    d = np.load(os.path.join(G, "decoder_logits_ref.npz"))
+    for seed in (1, 2, 3):
+        sd = BM.make_state_dict(seed, 0.5, 3.0)
+        enc = BM.make_encoder_output(seed, 6 + seed)
+        o = UnityOracle(BM.CFG, sd)
+        ids = torch.from_numpy(d[f"tokens_{seed}"])[None]
+        logits = o.project(o.decoder(o.embed_text(ids, 0), enc, None))[0]
+        assert logits.shape == d[f"logits_{seed}"].shape
+        assert np.abs(logits.numpy() - d[f"logits_{seed}"]).max() < 5e-3
+
+
+def test_beam_search_mechanics_match_reference_cpp():
+    """UnityOracle.beam_search against hypotheses returned by the UNMODIFIED `generate_sequence` of the C++ mirror
+    (fairseq2.cpp:1371-1608): bootstrap scoring of the prompt, incremental decoding with KV cache and its reordering,
+    first step from beam 0 only, top-2*beam candidates, EOS finalisation with length normalisation, stop at `beam` finished
+    hypotheses, descending order.  The mirror's double graph evaluation (see `mirror_recompute_defect`) is emulated so that
+    the comparison is hypothesis for hypothesis; scores are sums of softmax probabilities there, tolerance as above."""
+    import json
+    BM = _beam_model()
+    ref = json.load(open(os.path.join(G, "beam_search_ref.json")))
+    assert set(ref) == {sc["name"] for sc in BM.SCENARIOS}
+    n_hyps = 0
+    for sc in BM.SCENARIOS:
+        sd = BM.make_state_dict(sc["seed"], sc["eos_bias"], sc["gain"])
+        enc = BM.make_encoder_output(sc["seed"], sc["s_enc"])
+        o = UnityOracle(BM.CFG, sd)
+        hyps = o.beam_search(enc, None, sc["prefix"], beam=sc["beam"], soft_max=sc["soft"], hard_max=sc["hard"],
+                             len_penalty=sc["len_penalty"], mirror_recompute_defect=True)[0]
+        want = ref[sc["name"]]
+        assert len(hyps) == len(want), (sc["name"], len(hyps), len(want))
+        for (score, toks), w in zip(hyps, want):
+            assert toks == w["tokens"], (sc["name"], toks, w["tokens"])
+            assert abs(score - w["score"]) < 3e-3, (sc["name"], score, w["score"])
+        n_hyps += len(want)
+    assert n_hyps >= 30
