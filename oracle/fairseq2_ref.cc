@@ -14,6 +14,8 @@
 #include "fairseq2.h"
 
 // defined in fairseq2.cpp, not declared in its header
+extern "C" ggml_tensor* StandardTransformerEncoder_forward(fairseq2_model& model, const std::string& prefix, ggml_tensor* seqs,
+                                                           ggml_tensor* padding_mask);
 extern "C" ggml_tensor* StandardTransformerDecoder_forward(fairseq2_model& model, const std::string& prefix, ggml_tensor* seqs,
                                                            ggml_tensor* padding_mask, ggml_tensor* encoder_output,
                                                            ggml_tensor* encoder_padding_mask);
@@ -149,6 +151,29 @@ int fs2ref_decoder_logits(int n_tensors, const char** names, const float** data,
   ggml_free(ctx);
   ggml_free(wctx);
   return vocab;
+}
+
+// StandardTransformerEncoder_forward (fairseq2.cpp:955-977: pre-LN encoder layers + final LayerNorm) over one unpadded
+// sequence x [S][model_dim]; the T2U encoder of the path is this module.
+int fs2ref_encoder(int n_tensors, const char** names, const float** data, const std::int64_t* d0, const std::int64_t* d1,
+                   int n_modules, const char** modules, int n_layernorm, const char** layernorm_names, double ln_eps, int n_attn,
+                   const char** attn_names, int num_heads, int n_layers_norm_order, const char** layer_names, const char* prefix,
+                   const float* x, int seq_len, int model_dim, float* out) {
+  fairseq2_model model;
+  ggml_context* wctx = build_model(model, n_tensors, names, data, d0, d1, n_modules, modules, n_layernorm, layernorm_names, ln_eps,
+                                  n_attn, attn_names, num_heads, n_layers_norm_order, layer_names, 1);
+  ggml_context* ctx = make_ctx(256u << 20);
+  model.ctx = ctx;
+  ggml_tensor* seqs = ggml_new_tensor_3d(ctx, GGML_TYPE_F32, model_dim, seq_len, 1);
+  std::memcpy(seqs->data, x, ggml_nbytes(seqs));
+  ggml_tensor* y = StandardTransformerEncoder_forward(model, prefix, seqs, nullptr);
+  ggml_cgraph* gf = ggml_new_graph(ctx);
+  ggml_build_forward_expand(gf, y);
+  ggml_graph_compute_with_ctx(ctx, gf, 1);
+  std::memcpy(out, y->data, ggml_nbytes(y));
+  ggml_free(ctx);
+  ggml_free(wctx);
+  return 0;
 }
 
 }  // extern "C"

@@ -68,3 +68,34 @@ def make_encoder_output(seed: int, s_enc: int):
 def scaled_embedding(sd):
     """The converter bakes the embedding scale into the exported table (ggml_convert.py:370-382)."""
     return sd["text_decoder_frontend.embed.weight"] * math.sqrt(CFG["model_dim"])
+
+
+def make_encoder_state_dict(seed: int, layers: int = 2, prefix: str = "t2u_model.encoder"):
+    """Pre-LN Transformer encoder (the T2U encoder of the path) under the reference's parameter names."""
+    c = CFG
+    M, Fd = c["model_dim"], c["dec_ffn_dim"]
+    g = torch.Generator().manual_seed(3000 + seed)
+
+    def rnd(*shape, std=1.0):
+        return torch.randn(*shape, generator=g) * std
+
+    sd = {}
+
+    def lin(p, o, i):
+        sd[p + ".weight"] = rnd(o, i, std=(2.0 / (o + i)) ** 0.5 * 1.5)
+        sd[p + ".bias"] = rnd(o, std=0.05)
+
+    def ln(p):
+        sd[p + ".weight"] = 1.0 + rnd(M, std=0.1)
+        sd[p + ".bias"] = rnd(M, std=0.05)
+
+    for i in range(layers):
+        p = f"{prefix}.layers.{i}"
+        ln(p + ".self_attn_layer_norm")
+        for q in ("q_proj", "k_proj", "v_proj", "output_proj"):
+            lin(f"{p}.self_attn.{q}", M, M)
+        ln(p + ".ffn_layer_norm")
+        lin(p + ".ffn.inner_proj", Fd, M)
+        lin(p + ".ffn.output_proj", M, Fd)
+    ln(prefix + ".layer_norm")
+    return sd

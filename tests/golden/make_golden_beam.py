@@ -119,6 +119,34 @@ def main():
         logit_cases[f"logits_{seed}"] = reference_logits(lib, sd, enc, toks)
     np.savez_compressed(os.path.join(HERE, "decoder_logits_ref.npz"), **logit_cases)
     print("wrote decoder_logits_ref.npz", {k: v.shape for k, v in logit_cases.items()})
+    # ---- T2U encoder: StandardTransformerEncoder_forward (fairseq2.cpp:502-553, 955-977)
+    lib.fs2ref_encoder.restype = I
+    lib.fs2ref_encoder.argtypes = [I, PP, PP, PP, PP, I, PP, I, PP, D, I, PP, I, I, PP, C.c_char_p, PP, I, I, PP]
+    enc_cases = {}
+    for seed, S in ((1, 9), (2, 1), (3, 17)):
+        sd = BM.make_encoder_state_dict(seed)
+        names = sorted(sd)
+        arrs = [np.ascontiguousarray(sd[k].numpy().astype(np.float32)) for k in names]
+        n = len(names)
+        c_names = (C.c_char_p * n)(*[k.encode() for k in names])
+        c_data = (C.c_void_p * n)(*[a.ctypes.data for a in arrs])
+        d0 = (C.c_int64 * n)(*[a.shape[0] for a in arrs])
+        d1 = (C.c_int64 * n)(*[a.shape[1] if a.ndim == 2 else 0 for a in arrs])
+        layers = [f"t2u_model.encoder.layers.{i}" for i in range(2)]
+        attn = [l + ".self_attn" for l in layers]
+        lns = [f"{l}.{a}" for l in layers for a in ("self_attn_layer_norm", "ffn_layer_norm")] + ["t2u_model.encoder.layer_norm"]
+        modules = layers + attn + lns + [l + ".ffn" for l in layers]
+        keep = [(C.c_char_p * len(xs))(*[x.encode() for x in xs]) for xs in (modules, lns, attn, layers)]
+        x = torch.randn(S, BM.CFG["model_dim"], generator=torch.Generator().manual_seed(4000 + seed)).numpy().astype(np.float32)
+        y = np.zeros_like(x)
+        rc = lib.fs2ref_encoder(n, C.cast(c_names, PP), C.cast(c_data, PP), C.cast(d0, PP), C.cast(d1, PP), len(modules),
+                                C.cast(keep[0], PP), len(lns), C.cast(keep[1], PP), 1e-5, len(attn), C.cast(keep[2], PP),
+                                BM.CFG["num_heads"], len(layers), C.cast(keep[3], PP), b"t2u_model.encoder", x.ctypes.data, S,
+                                BM.CFG["model_dim"], y.ctypes.data)
+        assert rc == 0
+        enc_cases[f"x_{seed}"], enc_cases[f"y_{seed}"] = x, y
+    np.savez_compressed(os.path.join(HERE, "t2u_encoder_ref.npz"), **enc_cases)
+    print("wrote t2u_encoder_ref.npz", {k: v.shape for k, v in enc_cases.items()})
 
 
 if __name__ == "__main__":

@@ -164,6 +164,19 @@ def test_decoder_logits_match_reference_cpp():
         assert np.abs(logits.numpy() - d[f"logits_{seed}"]).max() < 5e-3
 
 
+def test_t2u_encoder_matches_reference_cpp():
+    """UnitYNART2UModel.encode's module (pre-LN encoder layers + final LayerNorm) against
+    StandardTransformerEncoder_forward of the C++ mirror (fairseq2.cpp:502-553, 955-977)."""
+    BM = _beam_model()
+    d = np.load(os.path.join(G, "t2u_encoder_ref.npz"))
+    for seed in (1, 2, 3):
+        cfg = dict(BM.CFG, t2u_enc_layers=2)
+        o = UnityOracle(cfg, BM.make_encoder_state_dict(seed))
+        x = torch.from_numpy(d[f"x_{seed}"])[None]
+        y = o.t2u_encoder(x, None)[0]
+        assert np.abs(y.numpy() - d[f"y_{seed}"]).max() < 2e-3
+
+
 def test_beam_search_mechanics_match_reference_cpp():
     """UnityOracle.beam_search against hypotheses returned by the UNMODIFIED `generate_sequence` of the C++ mirror
     (fairseq2.cpp:1371-1608): bootstrap scoring of the prompt, incremental decoding with KV cache and its reordering,
