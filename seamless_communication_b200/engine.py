@@ -65,6 +65,12 @@ class UnitYEngine:
         self.skinny_splits = tuple(int(v) for v in os.environ.get("SB_SKINNY_SPLITS", "4,8,16").split(","))  # qkv, attn, ffn2
         self.skinny_sites = set(os.environ.get("SB_SKINNY_SITES", "attn").split(","))  # of qkv, attn, ffn1, ffn2
         self.graph_kernels = 0  # kernels executed through CUDA-graph replays (bench.py: gpu_launches)
+        # SB_DECODER_FUSED=1: one persistent kernel per decoder step (sb_decoder_step, csrc/decoder_step.cu) instead of the
+        # per-op launch chain.  Opt-in: measured on B200 it is correct and deterministic but not faster (2.6-3.0 ms per step
+        # against 2.3 ms): a grid-wide phase barrier through L2 costs about as much as a kernel boundary inside a CUDA graph
+        # (profiles/r02_notes.md).
+        self.decode_fused = os.environ.get("SB_DECODER_FUSED", "0") != "0"
+        self.decode_timeline = os.environ.get("SB_DS_TIMELINE", "0") != "0"
 
     # ------------------------------------------------------------------------------------------ weight packing
     def _pack(self, sd):
@@ -133,6 +139,23 @@ class UnitYEngine:
             ln(f"{p}.encoder_decoder_attn_layer_norm"); mha(f"{p}.encoder_decoder_attn", fuse_qkv=False)
             ln(f"{p}.ffn_layer_norm"); lin(f"{p}.ffn.inner_proj"); lin(f"{p}.ffn.output_proj")
         ln("text_decoder.layer_norm")
+        # The persistent decoder-step kernel (csrc/decoder_step.cu) reads all layers through two TMA descriptors: stack the
+        # decoder matrices with K = model_dim ([layer][q|k|v, self out, cross q, cross out, FFN inner]) and the FFN output
+        # matrices (K = ffn_dim); the per-layer entries of `w` become views of the stacks (no second copy).
+        M_, F_ = c.model_dim, c.dec_ffn_dim
+        names = (".self_attn.qkv", ".self_attn.output_proj", ".encoder_decoder_attn.q_proj", ".encoder_decoder_attn.output_proj",
+                 ".ffn.inner_proj")
+        self.dec_w_dim = torch.empty((c.dec_layers * (6 * M_ + F_), M_), dtype=F16, device=dev)
+        self.dec_w_ffn = torch.empty((c.dec_layers * M_, F_), dtype=F16, device=dev)
+        for i in range(c.dec_layers):
+            p, r = f"text_decoder.layers.{i}", i * (6 * M_ + F_)
+            for n in names:
+                t = w[p + n + ".w"]
+                self.dec_w_dim[r:r + t.shape[0]].copy_(t)
+                w[p + n + ".w"] = self.dec_w_dim[r:r + t.shape[0]]
+                r += t.shape[0]
+            self.dec_w_ffn[i * M_:(i + 1) * M_].copy_(w[p + ".ffn.output_proj.w"])
+            w[p + ".ffn.output_proj.w"] = self.dec_w_ffn[i * M_:(i + 1) * M_]
         if self.has_t2u:
             for i in range(c.t2u_enc_layers):
                 p = f"t2u_model.encoder.layers.{i}"
@@ -265,6 +288,11 @@ class UnitYEngine:
         R, stream = st["R"], ops._stream()
         x, h, part = st["x"], st["h"], st["partials"]
         w = self.w
+        if st.get("ds_launch") is not None:
+            # embedding frontend + all decoder layers + final LayerNorm (+ hist[step] = h) in one persistent kernel
+            check(lib.sb_decoder_step(C.byref(st["ds_launch"]), stream), "sb_decoder_step")
+            ops.gemm(h, w["text_embed"], c.text_vocab, None, out=st["logits"], out_f32=True)
+            return
         check(lib.sb_embed_step(st["seqs"].data_ptr(), st["ML"], st["step"].data_ptr(), w["text_embed"].data_ptr(),
                                 self.pos.data_ptr(), math.sqrt(M), x.buf.data_ptr(), R, M, stream), "sb_embed_step")
         self._ln(x, "text_decoder.layers.0.self_attn_layer_norm", out=h)
@@ -324,7 +352,7 @@ class UnitYEngine:
         """Static buffers + captured CUDA graphs of one decoder step, cached per problem shape so that repeated
         predict() calls replay the same graphs (the reference rebuilds its generator per call, translator.py:179-186;
         construction here stays cheap after the first call)."""
-        key = (B, S_enc, ML, beam, P, has_lens, use_graph, slot)
+        key = (B, S_enc, ML, beam, P, has_lens, use_graph, slot, self.decode_fused)
         st = self._graphs.get(key)
         if st is not None:
             return st
@@ -387,10 +415,62 @@ class UnitYEngine:
         d.fin_seqs, d.active, d.n_active = fin["seqs"].data_ptr(), fin["active"].data_ptr(), fin["n_active"].data_ptr()
         d.fin_anc = fin["anc"].data_ptr()
         st["beam_desc"] = d
+        st["ds_launch"] = self._decoder_plan(st) if self.decode_fused else None
         st["g_fwd"] = st["g_sel"] = None
         st["n_fwd"] = st["n_sel"] = 0
         self._graphs[key] = st
         return st
+
+    def _decoder_plan(self, st):
+        """Device-side plan of the persistent decoder-step kernel for one search state (workspace sizes come from
+        sb_decoder_plan_query; every pointer in the plan is a static buffer of `st`)."""
+        lib = _lib.load()
+        c, M, dev, w = self.cfg, self.M, self.device, self.w
+        info = _lib.DecoderPlanInfo()
+        check(lib.sb_decoder_plan_query(c.dec_layers, M, c.dec_ffn_dim, st["R"], st["beam"], 0, C.byref(info)), "sb_decoder_plan_query")
+        st["ds_info"] = info
+        st["ds_part_qkv"] = torch.empty(int(info.part_qkv_floats), dtype=torch.float32, device=dev)
+        st["ds_part"] = torch.empty(int(info.part_floats), dtype=torch.float32, device=dev)
+        st["ds_counters"] = torch.zeros(int(info.counters_len), dtype=I32, device=dev)
+        # head-major copies of the static encoder K / V ([B][H][S_enc][64]); the self-attention cache is head-major as well
+        # ([slot][H][max_len][64], same bytes as st["kc"] / st["vc"]): one hypothesis reads a few contiguous runs
+        B = st["B"]
+        st["cross_k_hm"] = [torch.empty((B, self.H, st["S_enc"], 64), dtype=F16, device=dev) for _ in range(c.dec_layers)]
+        st["cross_v_hm"] = [torch.empty((B, self.H, st["S_enc"], 64), dtype=F16, device=dev) for _ in range(c.dec_layers)]
+        st["ds_timeline"] = (torch.zeros((int(info.groups), int(info.n_phases), 8), dtype=torch.int64, device=dev)
+                             if self.decode_timeline else None)
+        layers = (_lib.DecoderLayerDesc * c.dec_layers)()
+        for i in range(c.dec_layers):
+            p, L = f"text_decoder.layers.{i}", layers[i]
+            last = i + 1 == c.dec_layers
+            nxt = "text_decoder.layer_norm" if last else f"text_decoder.layers.{i + 1}.self_attn_layer_norm"
+            for field, name in (("qkv", ".self_attn.qkv"), ("out", ".self_attn.output_proj"),
+                                ("cq", ".encoder_decoder_attn.q_proj"), ("co", ".encoder_decoder_attn.output_proj"),
+                                ("ffn1", ".ffn.inner_proj"), ("ffn2", ".ffn.output_proj")):
+                setattr(L, field + "_b", w[p + name + ".b"].data_ptr())
+            L.ca_ln_w, L.ca_ln_b = (w[p + ".encoder_decoder_attn_layer_norm" + s].data_ptr() for s in (".w", ".b"))
+            L.ffn_ln_w, L.ffn_ln_b = (w[p + ".ffn_layer_norm" + s].data_ptr() for s in (".w", ".b"))
+            L.next_ln_w, L.next_ln_b = w[nxt + ".w"].data_ptr(), w[nxt + ".b"].data_ptr()
+            L.k_cache, L.v_cache = st["kc"][i].data_ptr(), st["vc"][i].data_ptr()
+            L.cross_k, L.cross_v = st["cross_k_hm"][i].data_ptr(), st["cross_v_hm"][i].data_ptr()
+        d = _lib.DecoderPlanDesc()
+        d.layers, d.dim, d.ffn_dim, d.heads, d.rows, d.beam, d.groups = c.dec_layers, M, c.dec_ffn_dim, self.H, st["R"], st["beam"], int(info.groups)
+        d.max_len, d.s_enc = st["ML"], st["S_enc"]
+        d.layer = layers
+        d.w_dim_stack, d.w_ffn_stack = self.dec_w_dim.data_ptr(), self.dec_w_ffn.data_ptr()
+        d.ln0_w, d.ln0_b = (w["text_decoder.layers.0.self_attn_layer_norm" + s].data_ptr() for s in (".w", ".b"))
+        d.embed, d.pos, d.embed_scale = w["text_embed"].data_ptr(), self.pos.data_ptr(), math.sqrt(M)
+        d.seqs, d.seqs_ld, d.anc, d.anc_ld = st["seqs"].data_ptr(), st["ML"], st["anc"].data_ptr(), st["ML"]
+        d.step_ptr, d.enc_lens = st["step"].data_ptr(), ops._p(st["enc_lens"])
+        d.x, d.h, d.att, d.ffn_act = (st[k].buf.data_ptr() for k in ("x", "h", "att", "ffn"))
+        d.part_qkv, d.part_qkv_floats = st["ds_part_qkv"].data_ptr(), int(info.part_qkv_floats)
+        d.part, d.part_floats = st["ds_part"].data_ptr(), int(info.part_floats)
+        d.hist = st["hist"].data_ptr()
+        d.counters, d.counters_len = st["ds_counters"].data_ptr(), int(info.counters_len)
+        d.timeline = ops._p(st["ds_timeline"])
+        launch = _lib.DecoderLaunch()
+        check(lib.sb_decoder_plan_init(C.byref(d), C.byref(launch)), "sb_decoder_plan_init")
+        return launch
 
     def _capture(self, st):
         """Capture the forward and the select halves of a decoder step (all pointers/shapes static)."""
@@ -433,6 +513,11 @@ class UnitYEngine:
             st["enc_lens"].copy_(enc_lens)
         for i in range(c.dec_layers):
             self._lin(enc, f"text_decoder.layers.{i}.encoder_decoder_attn.kv", 2 * M, out=st["cross_kv"][i])
+            if st.get("ds_launch") is not None:
+                kv = st["cross_kv"][i].buf
+                check(_lib.load().sb_kv_heads_major(kv.data_ptr(), kv.stride(0), st["B"], st["S_enc"], self.H,
+                                                    st["cross_k_hm"][i].data_ptr(), st["cross_v_hm"][i].data_ptr(), ops._stream()),
+                      "sb_kv_heads_major")
         self._search_reset(st, prefix)
         if use_graph and st["g_fwd"] is None:
             self._capture(st)

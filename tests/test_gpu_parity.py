@@ -43,6 +43,12 @@ def tiny():
                 uo=UnityOracle(cfg.to_dict(), sd, toks), vo=VocoderOracle(vc.to_dict(), vsd))
 
 
+@pytest.fixture(scope="module")
+def small():
+    from seamless_communication_b200.models.unity import load_unity_model
+    return load_unity_model("small_v2", seed=7, dec_gain=4.0)
+
+
 # ------------------------------------------------------------------------------------------------ sb_gemm
 @pytest.mark.parametrize("m,n,k", [(128, 128, 64), (300, 200, 1024), (160, 3072, 1024), (1000, 1024, 4096), (513, 72, 160),
                                    (77, 10082, 128), (2000, 16, 16)])
@@ -351,6 +357,54 @@ def test_beam_search_sentence_groups_on_streams_equal_single_group(tiny, monkeyp
         assert torch.equal(out[1][1], out[g][1])
 
 
+@pytest.mark.parametrize("which", ["tiny", "small"])
+def test_persistent_decoder_step_equals_launch_chain(tiny, small, which):
+    """sb_decoder_step (one persistent kernel per step: csrc/decoder_step.cu) against the per-op launch chain it
+    replaces, on the same search: the final-LayerNorm state of every step within fp16 accumulation-order noise, the
+    same hypotheses (or a margin-audited near tie), and the K/V cache written identically up to rounding."""
+    from seamless_communication_b200.ops import Seq
+    eng = (tiny["model"] if which == "tiny" else small).engine
+    cfg = eng.cfg
+    torch.manual_seed(21)
+    M, S_enc, B, beam = cfg.model_dim, 13, (7 if which == "tiny" else 32), 5
+    e = Seq(B, S_enc, M, buf=torch.randn(B * S_enc, M, device=dev).half())
+    lens = torch.randint(3, S_enc + 1, (B,), dtype=torch.int32, device=dev)
+    lens[0] = S_enc
+    prefix = [cfg.text_eos, eng.text_tokenizer.lang_index("spa")]
+    out = {}
+    old = eng.decode_fused
+    try:
+        for fused in (False, True):
+            eng.decode_fused = fused
+            hyps = eng.beam_search(e, lens, prefix, beam=beam, soft_max=(1, 9), hard_max=40)
+            st = eng._last_search_states[0]
+            assert (st["ds_launch"] is not None) == fused
+            n = min(len(h[0][1]) for h in hyps) - 1
+            kc = st["kc"][cfg.dec_layers - 1]
+            R = st["R"]
+            # the launch chain keeps K time-major [t][slot][M], the persistent kernel head-major [slot][head][t][64]
+            kc = (kc.view(R, eng.H, st["ML"], 64).permute(2, 0, 1, 3).reshape(st["ML"], R, M) if fused else kc)[:n]
+            out[fused] = (hyps, st["hist"][:n].clone(), kc.clone())
+    finally:
+        eng.decode_fused = old
+    (h0, hist0, kc0), (h1, hist1, kc1) = out[False], out[True]
+    # step 0..1 see identical inputs on both paths (same prefix): states agree to accumulation-order noise
+    assert rel(hist1[:2], hist0[:2]) < 4e-3 and rel(kc1[:2], kc0[:2]) < 4e-3
+    same = sum(a[0][1] == b[0][1] for a, b in zip(h0, h1))
+    assert same >= B - max(1, B // 8), f"only {same}/{B} best hypotheses agree"
+    for a, b in zip(h0, h1):
+        assert abs(a[0][0] - b[0][0]) < 2e-2
+    # determinism of the persistent kernel: a second search is bit-identical
+    eng.decode_fused = True
+    try:
+        hyps2 = eng.beam_search(e, lens, prefix, beam=beam, soft_max=(1, 9), hard_max=40)
+        st = eng._last_search_states[0]
+        assert [h[0][1] for h in hyps2] == [h[0][1] for h in h1]
+        assert torch.equal(st["hist"][:hist1.shape[0]], hist1)
+    finally:
+        eng.decode_fused = old
+
+
 def test_beam_search_ragged_encoder_and_early_eos(tiny):
     """Sentences with different encoder lengths, searched together, equal the same sentences searched alone."""
     from seamless_communication_b200.ops import Seq
@@ -493,12 +547,6 @@ def test_translator_predict_s2st_and_s2tt(tiny):
 
 
 # ------------------------------------------------------------------------------------------------ properties at full width
-@pytest.fixture(scope="module")
-def small():
-    from seamless_communication_b200.models.unity import load_unity_model
-    return load_unity_model("small_v2", seed=7, dec_gain=4.0)
-
-
 def test_full_width_properties_permutation_padding_determinism(small, ops):
     """M=1024 / 16 heads / 10 s audio (the BASELINE tile shapes), too big for the CPU oracle in a unit test:
     utterances are independent, so (a) permuting the batch permutes the encoder output bit-exactly, (b) running an
