@@ -573,6 +573,162 @@ def test_full_width_properties_permutation_padding_determinism(small, ops):
     assert torch.isfinite(e).all() and e.float().std() > 0.1
 
 
+# ------------------------------------------------------------------------------------------------ BASELINE width (config 3)
+def _replay_search_on_logits(eng, trace, prefix, beam, V, len_penalty=1.0):
+    """Drive the INTEGER half of the search (sb_logits_topk -> sb_beam_step -> sb_step_advance, exactly as
+    engine._decoder_step_select does) with the oracle's fp32 logits, step by step, for one sentence.  Returns what the
+    device decided at every step: (parent beam indices, next tokens), and the finished hypotheses."""
+    import ctypes as Ct
+    from seamless_communication_b200 import _lib
+    from seamless_communication_b200._lib import BeamDesc, check
+    lib = _lib.load()
+    st = torch.cuda.current_stream().cuda_stream
+    ML, P, R, c = trace["max_len"], len(prefix), beam, eng.cfg
+    K = min(2 * beam + 1, 16)
+    ld = (V + 7) // 8 * 8
+    i32 = dict(dtype=torch.int32, device=dev)
+    seqs, anc = torch.zeros((R, ML), **i32), torch.arange(R, **i32)[:, None].repeat(1, ML).contiguous()
+    seqs[:, :P] = torch.tensor(prefix, **i32)
+    scores = torch.zeros((R, ML), device=dev)
+    scores[:, :P] = trace["prefix_scores"].to(dev)
+    step = torch.full((1,), P - 1, **i32)
+    logits = torch.zeros((R, ld), device=dev)
+    cv, ci, el = torch.empty((R, K), device=dev), torch.empty((R, K), **i32), torch.empty((R,), device=dev)
+    fin = dict(count=torch.zeros(1, **i32), score=torch.full((1, beam), -math.inf, device=dev), len=torch.zeros((1, beam), **i32),
+               seqs=torch.zeros((1, beam, ML), **i32), active=torch.ones(1, **i32), n_active=torch.ones(1, **i32),
+               anc=torch.zeros((1, beam, ML), **i32))
+    d = BeamDesc()
+    d.batch, d.beam, d.max_len, d.vocab, d.K = 1, beam, ML, V, K
+    d.step_ptr, d.prefix_len, d.eos_idx, d.min_len, d.len_penalty = step.data_ptr(), P, c.text_eos, 1, len_penalty
+    d.cand_val, d.cand_idx, d.eos_lprob = cv.data_ptr(), ci.data_ptr(), el.data_ptr()
+    d.seqs, d.scores, d.anc = seqs.data_ptr(), scores.data_ptr(), anc.data_ptr()
+    d.fin_count, d.fin_score, d.fin_len = fin["count"].data_ptr(), fin["score"].data_ptr(), fin["len"].data_ptr()
+    d.fin_seqs, d.active, d.n_active, d.fin_anc = fin["seqs"].data_ptr(), fin["active"].data_ptr(), fin["n_active"].data_ptr(), fin["anc"].data_ptr()
+    decisions = []
+    for s, lg in enumerate(trace["logits"]):
+        pos = P - 1 + s
+        assert seqs[:, pos].tolist() == trace["inputs"][s].tolist(), f"step {s}: device rows feed other tokens than the oracle's"
+        logits[:, :V] = lg.to(dev)
+        check(lib.sb_logits_topk(logits.data_ptr(), ld, R, V, c.text_pad, c.text_eos, c.text_unk, 0.0, K, cv.data_ptr(), ci.data_ptr(),
+                                 el.data_ptr(), st))
+        check(lib.sb_beam_step(Ct.byref(d), st))
+        check(lib.sb_step_advance(step.data_ptr(), st))
+        if int(fin["active"].item()) == 0:
+            break
+        decisions.append((anc[:, pos].tolist(), seqs[:, pos + 1].tolist()))
+    n = int(fin["count"].item())
+    finished = [(float(fin["score"][0, j]), fin["seqs"][0, j, :int(fin["len"][0, j])].tolist()) for j in range(n)]
+    return decisions, finished
+
+
+def test_search_integer_half_is_bit_exact_on_oracle_logits(tiny):
+    """Given the SAME fp32 logits, top-K selection, beam bookkeeping, EOS handling and finalisation order must be
+    bit-identical to the oracle's (whose mechanics are pinned against the reference's C++ generate_sequence): parents,
+    tokens, finished hypotheses and their order, at every step."""
+    cfg, uo, eng = tiny["cfg"], tiny["uo"], tiny["model"].engine
+    waves = S.make_waveforms(2, 32000, seed=77)
+    fb = torch.stack([o_fbank(w) for w in waves])
+    for sentence in (0, 1):
+        trace = {"sentence": sentence}
+        uo.generate(fb, None, "spa", hard_max=30, output_units=False, trace=trace)
+        prefix = [cfg.text_eos, tiny["toks"][0].lang_index("spa")]
+        decisions, finished = _replay_search_on_logits(eng, trace, prefix, 5, cfg.text_vocab)
+        assert len(decisions) == len(trace["beam_idx"])
+        for s, (parents, toks) in enumerate(decisions):
+            assert parents == trace["beam_idx"][s].tolist(), f"step {s}: parent beams differ"
+            if s + 1 < len(trace["inputs"]):
+                assert toks == trace["inputs"][s + 1].tolist(), f"step {s}: tokens differ"
+        assert [f[1] for f in finished] == [f[1] for f in trace["finished"]]
+        assert np.allclose([f[0] for f in finished], [f[0] for f in trace["finished"]], rtol=0, atol=1e-5)
+
+
+@pytest.fixture(scope="module")
+def base():
+    """seamlessM4T_v2_large + vocoder_v2 with the bench's seeded random-init weights, and the fp32 oracle on the same
+    state dicts (BASELINE config 3: M=1024, 16 heads, 24+24 layers, V=256 102)."""
+    from seamless_communication_b200.inference import Translator
+    from seamless_communication_b200.models.unity import load_unity_model
+    from seamless_communication_b200.models.vocoder import load_vocoder_model
+    cfg, vc = C.base_v2(), C.base_vocoder()
+    sd = S.make_unity_state_dict(cfg, seed=0, dec_gain=4.0)
+    vsd = S.make_vocoder_state_dict(vc, seed=1)
+    toks = S.make_tokenizers(cfg)
+    model = load_unity_model("seamlessM4T_v2_large", device=dev, state_dict=sd, tokenizers=toks)
+    voc = load_vocoder_model("vocoder_v2", device=dev, state_dict=vsd)
+    torch.set_num_threads(min(32, os.cpu_count() or 1))
+    return dict(cfg=cfg, toks=toks, model=model, voc=voc, tr=Translator(model, voc, device=dev),
+                uo=UnityOracle(cfg.to_dict(), sd, toks), vo=VocoderOracle(vc.to_dict(), vsd))
+
+
+def test_full_width_s2st_matches_oracle(base, ops):
+    """The whole S2ST path at the BASELINE width against the fp32 CPU oracle on the bench's first utterance (seed 1234,
+    10 s, beam 5, hard_max_seq_len 102): encoder output, teacher-forced decoder states and logits, the search (ids equal
+    or a margin-audited near tie; the integer half bit-exact on the oracle's own logits), units from the oracle's decoder
+    states, waveform from the oracle's units.  Tolerances: fp16 storage / fp32 accumulation against fp32."""
+    from seamless_communication_b200.ops import Seq
+    cfg, uo, vo, eng, voc, tr = base["cfg"], base["uo"], base["vo"], base["model"].engine, base["voc"], base["tr"]
+    M, HARD_MAX = cfg.model_dim, 102
+    waves = S.make_waveforms(1, 160000, seed=1234)
+    trace = {"sentence": 0}
+    with torch.inference_mode():
+        ref = s2st(uo, vo, waves, "spa", 25, 45, hard_max=HARD_MAX, trace=trace)
+    # --- a1-a6: fbank + encoder
+    src = tr.fbank_batch(waves.to(dev))
+    assert (src["seqs"][0].float().cpu() - ref["fbank"][0]).abs().max() < 2e-2  # fp16 log-mel (|x| up to ~8) vs fp32
+    enc, lens = eng.encode_speech(src["seqs"], None)
+    err_enc = rel(enc.buf.view(1, -1, M), ref["enc"])
+    assert err_enc < 5e-3, f"encoder output rel err {err_enc}"
+    # --- a8/a9: teacher-forced decoder states and logits over the oracle's best hypothesis
+    ids = ref["text_ids"][0]
+    assert len(ids) == HARD_MAX  # random weights: no early EOS, forced EOS at max_len - 2
+    ts = torch.tensor(ids[:-1])[None]
+    tl = torch.tensor([len(ids) - 1], dtype=torch.int32, device=dev)
+    enc_o = Seq(1, ref["enc"].shape[1], M, buf=ref["enc"].to(dev).half().reshape(-1, M).contiguous())
+    dec = eng.decode_full(ts.to(dev), tl, enc_o, None)
+    err_dec = rel(dec.buf.view(1, -1, M), ref["dec_out"])
+    assert err_dec < 5e-3, f"decoder states rel err {err_dec}"
+    lg = ops.gemm_raw(dec.buf, eng.w["text_embed"], cfg.text_vocab, out_f32=True).float().cpu()
+    with torch.inference_mode():
+        lg_o = uo.project(ref["dec_out"])[0]
+    err_lg = (lg - lg_o).abs().max().item()
+    assert err_lg < 5e-2, f"logits abs err {err_lg} (std {lg_o.std():.2f})"
+    # --- a7: the search itself (device-resident, CUDA-graph replayed) from the oracle's encoder output
+    prefix = [cfg.text_eos, base["toks"][0].lang_index("spa")]
+    hyps = eng.beam_search(enc_o, None, prefix, beam=5, hard_max=HARD_MAX)
+    assert len(hyps[0]) == len(ref["hyps"][0]) == 5
+    if hyps[0][0][1] != ids:  # margin audit under the oracle's own scoring
+        with torch.inference_mode():
+            assert abs(_oracle_score(uo, ref["enc"], hyps[0][0][1]) - ref["hyps"][0][0][0]) < 2e-2
+    assert abs(hyps[0][0][0] - ref["hyps"][0][0][0]) < 2e-2
+    same_prefix = next((i for i, (a, b) in enumerate(zip(hyps[0][0][1], ids)) if a != b), len(ids))
+    assert same_prefix >= 8, f"search diverges from the oracle after {same_prefix} tokens"
+    # the harvested states of the winning hypothesis equal the teacher-forced pass over it
+    got = eng.harvest_decoder_states([len(hyps[0][0][1]) - 1])
+    if hyps[0][0][1] == ids:
+        assert rel(got.buf.view(1, -1, M), ref["dec_out"]) < 5e-3
+    # --- integer half, bit-exact on the oracle's logits at V = 256 102
+    decisions, finished = _replay_search_on_logits(eng, trace, prefix, 5, cfg.text_vocab)
+    for s, (parents, toks) in enumerate(decisions):
+        assert parents == trace["beam_idx"][s].tolist(), f"step {s}: parent beams differ"
+        if s + 1 < len(trace["inputs"]):
+            assert toks == trace["inputs"][s + 1].tolist(), f"step {s}: tokens differ"
+    assert [f[1] for f in finished] == [f[1] for f in trace["finished"]]
+    # --- a11-a14: units from the oracle's decoder states (upstream near ties cannot mask a defect)
+    dseq = Seq(1, ref["dec_out"].shape[1], M, lens=tl, buf=ref["dec_out"].to(dev).half().reshape(-1, M).contiguous())
+    units, ulens, _ = eng.t2u(dseq, ref["text_seqs"].to(dev), durations=ref["dur"])
+    assert ulens.tolist() == ref["unit_lens"].tolist()
+    n = int(ref["unit_lens"][0])
+    assert n == 495  # 99 subwords x 5 characters, duration 1 each (SURVEY 8d)
+    diff = int((units[0, :n].cpu() != ref["units"][0, :n]).sum())
+    assert diff <= 1, f"{diff} unit ids differ from the oracle"
+    # --- a15/a16: waveform from the oracle's units, and the trimming rule
+    wav = voc(ref["units"].to(dev), "spa", -1, dur_prediction=False)
+    err_wav = (wav.float().cpu() - ref["wav_full"]).abs().max().item()
+    assert err_wav < 5e-3, f"waveform abs err {err_wav}"
+    print(f"full width: enc {err_enc:.1e} dec {err_dec:.1e} logits {err_lg:.1e} units diff {diff} wav {err_wav:.1e} "
+          f"search common prefix {same_prefix}/{len(ids)}")
+
+
 # ------------------------------------------------------------------------------------------------ a17 monotonic decoder
 def test_monotonic_decoder_pchoose_and_policy_match_oracle():
     from seamless_communication_b200.models.monotonic_decoder import load_monotonic_decoder_model
