@@ -507,8 +507,10 @@ static int launch(const sb_gemm_t* g, cudaStream_t st, int splits = 1, long long
   int kb_per = 0;
   if (splits > 1) {
     const int kb_total = g->taps * ((g->c_in + BK - 1) / BK);
-    kb_per = (kb_total + splits - 1) / splits;
-    splits = (kb_total + kb_per - 1) / kb_per;
+    // consumers (sb_splitk_reduce_ln, the decode attention kernels) sum exactly the caller's `splits` slices: an uneven split
+    // would leave slices unwritten
+    SB_REQUIRE(kb_total % splits == 0, SB_EINVAL, "sb_gemm_splitk: %d k-blocks are not divisible by %d splits", kb_total, splits);
+    kb_per = kb_total / splits;
     args.kb_per_split = kb_per;
     args.slice_rows = slice_rows > 0 ? slice_rows : g->m;
     // one tensor map covers all slices, so an M-tail tile of slice z would spill into slice z+1 unless the slice

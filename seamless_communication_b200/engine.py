@@ -14,6 +14,7 @@ Weight packing (one-time, at load):
 """
 from __future__ import annotations
 
+import collections
 import ctypes as C
 import math
 import os
@@ -57,7 +58,7 @@ class UnitYEngine:
         self.pos = sinusoid_table(cfg.max_seq_len, self.M).to(self.device)
         if self.has_t2u:
             self._build_char_tables()
-        self._graphs = {}
+        self._graphs = collections.OrderedDict()
         self._search_streams = []
         self.search_groups = 1  # concurrent sentence groups in beam_search (see _search_group_count)
         self.decode_prefetch = os.environ.get("SB_DECODE_PREFETCH", "1") != "0"
@@ -355,11 +356,14 @@ class UnitYEngine:
         key = (B, S_enc, ML, beam, P, has_lens, use_graph, slot, self.decode_fused)
         st = self._graphs.get(key)
         if st is not None:
+            self._graphs.move_to_end(key)
             return st
         c, M, dev = self.cfg, self.M, self.device
         R = B * beam
         K = min(2 * beam + 1, 16)
-        assert 2 * beam <= 16, "beam size above 8 is not supported by the top-K kernel"
+        # the top-K kernel returns at most 16 candidates per row and the step needs 2*beam + 1 (one spare for a blocked EOS)
+        if 2 * beam + 1 > 16:
+            raise ValueError(f"beam_size {beam} is not supported by the top-K kernel (at most 7)")
         st = dict(R=R, ML=ML, beam=beam, K=K, S_enc=S_enc, B=B, P=P, unk_penalty=0.0)
         st["enc_lens"] = torch.zeros(B, dtype=I32, device=dev) if has_lens else None
         st["cross_kv"] = [Seq(B, S_enc, 2 * M) for _ in range(c.dec_layers)]
@@ -419,7 +423,46 @@ class UnitYEngine:
         st["g_fwd"] = st["g_sel"] = None
         st["n_fwd"] = st["n_sel"] = 0
         self._graphs[key] = st
+        self._evict_search_states(keep=key)
         return st
+
+    @staticmethod
+    def _state_bytes(st) -> int:
+        seen, total = set(), 0
+
+        def walk(v):
+            nonlocal total
+            if isinstance(v, torch.Tensor):
+                p = v.untyped_storage().data_ptr()
+                if p not in seen:
+                    seen.add(p)
+                    total += v.untyped_storage().nbytes()
+            elif isinstance(v, Seq):
+                walk(v.buf)
+            elif isinstance(v, dict):
+                for x in v.values():
+                    walk(x)
+            elif isinstance(v, (list, tuple)):
+                for x in v:
+                    walk(x)
+        walk(st)
+        return total
+
+    def _evict_search_states(self, keep):
+        """The cache is keyed by problem shape (S_enc and max_len follow the audio length), one entry holds the KV caches,
+        the history and two CUDA graphs (~4.8 GB at 32 sentences x beam 5): least-recently-used entries are dropped once
+        the total exceeds SB_SEARCH_CACHE_GB (default 12), so a service fed variable-length audio cannot grow without
+        bound (the reference frees its search state after every call)."""
+        budget = float(os.environ.get("SB_SEARCH_CACHE_GB", "12")) * 2 ** 30
+        sizes = {k: self._state_bytes(v) for k, v in self._graphs.items()}
+        total = sum(sizes.values())
+        for k in list(self._graphs.keys()):
+            if total <= budget or len(self._graphs) <= 1:
+                break
+            if k == keep or any(k is not keep and st is self._graphs[k] for st in (getattr(self, "_last_search_states", None) or [])):
+                continue
+            total -= sizes[k]
+            del self._graphs[k]
 
     def _decoder_plan(self, st):
         """Device-side plan of the persistent decoder-step kernel for one search state (workspace sizes come from
@@ -505,8 +548,9 @@ class UnitYEngine:
         c, M = self.cfg, self.M
         st["unk_penalty"] = float(unk_penalty)
         d = st["beam_desc"]
-        if (d.min_len, d.len_penalty) != (min_seq_len, len_penalty) or st.get("unk_cap") != float(unk_penalty):
+        if st.get("opts_cap") != (min_seq_len, float(len_penalty)) or st.get("unk_cap") != float(unk_penalty):
             d.min_len, d.len_penalty = min_seq_len, len_penalty
+            st["opts_cap"] = (min_seq_len, float(len_penalty))  # compared as Python values: c_float rounds 0.9 and would recapture every call
             st["g_fwd"] = st["g_sel"] = None  # scalar options are baked into the captured select graph
             st["unk_cap"] = float(unk_penalty)
         if enc_lens is not None:
@@ -713,6 +757,9 @@ class UnitYEngine:
                                    char_lens.data_ptr(), char_seqs.data_ptr(), max_c, char_seq_lens.data_ptr(), stream),
               "sb_text_to_chars")
         Cn = max(int(char_seq_lens.max().item()), 1)  # host sync #1 (the reference syncs here too: .item() at :231)
+        if Cn > c.max_seq_len:  # fairseq2's position encoder raises here; the kernel would read past the sinusoid table
+            raise ValueError(f"The input sequence length must be less than or equal to the maximum sequence length "
+                             f"({c.max_seq_len}), but is {Cn} instead.")
         P = "t2u_model.decoder_frontend"
         y = Seq(B, Cn, M, halo=1, lens=char_seq_lens)
         check(lib.sb_upsample_add(t2u_enc.buf.data_ptr(), t2u_enc.Tp, t2u_enc.PH, L, char_lens.data_ptr(),
@@ -731,6 +778,9 @@ class UnitYEngine:
             dur = durations.to(device=dev, dtype=I32).contiguous()
         unit_lens = dur.sum(dim=1).to(I32)
         U = max(int(unit_lens.max().item()), 1)  # host sync #2 (reference: length_regulator.py:30)
+        if U > c.max_seq_len:
+            raise ValueError(f"The input sequence length must be less than or equal to the maximum sequence length "
+                             f"({c.max_seq_len}), but is {U} instead.")
         halo = (c.fft_kernel - 1) // 2
         z = Seq(B, U, M, halo=halo, lens=unit_lens)
         check(lib.sb_upsample_add(y.buf.data_ptr(), y.Tp, y.PH, Cn, dur.data_ptr(), z.buf.data_ptr(), z.Tp, z.PH, U, B, M,
@@ -820,6 +870,12 @@ class VocoderEngine:
         # NOTE: every tensor whose data_ptr() is handed to a kernel must stay referenced until after the launch;
         # a temporary freed earlier can be re-issued by the caching allocator to the next allocation.
         units_i = units.to(I32).contiguous()
+        if os.environ.get("SB_CHECK_UNITS", "1") != "0":
+            # torch's embedding would assert on an id outside the table; the gather kernel would read out of bounds.
+            # UnitTokenDecoder maps control / language symbols to negative ids or ids >= num_embeddings (unit_tokenizer.py:231-238)
+            lo, hi = int(units_i.min().item()), int(units_i.max().item())
+            if lo < 0 or hi >= c.num_embeddings:
+                raise IndexError(f"unit id out of range for the vocoder's {c.num_embeddings}-entry table (min {lo}, max {hi})")
         lang_t = torch.tensor(lang_idx, dtype=I32, device=dev)
         spkr_t = torch.tensor(spkr_idx, dtype=I32, device=dev)
         check(lib.sb_vocoder_embed(units_i.data_ptr(), U, B, w["dict"].data_ptr(), c.embedding_dim,

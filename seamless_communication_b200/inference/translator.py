@@ -51,10 +51,17 @@ class Translator:
         if isinstance(model_name_or_card, UnitYModel):
             self.model = model_name_or_card
         else:
+            if text_tokenizer is not None and "tokenizers" not in model_kw:
+                # the engine's T2U character tables and the prefix ids are built from ITS tokenizer pair: a different decode-side
+                # tokenizer would silently produce wrong units (reference: one tokenizer object serves both, translator.py:118-127)
+                raise ValueError("pass tokenizers=(text_tokenizer, char_tokenizer) so that the engine is built with the same "
+                                 "tokenizer, or build the UnitYModel yourself")
             self.model = load_unity_model(model_name_or_card, device=self.device, dtype=dtype, with_t2u=with_t2u, **model_kw)
         self.model.eval()
         self.dtype = dtype
-        self.text_tokenizer = text_tokenizer or self.model.engine.text_tokenizer
+        if text_tokenizer is not None and text_tokenizer is not self.model.engine.text_tokenizer:
+            raise ValueError("text_tokenizer differs from the tokenizer the model's engine was built with")
+        self.text_tokenizer = self.model.engine.text_tokenizer
         self.unit_tokenizer: Optional[UnitTokenizer] = None
         if self.model.t2u_model is not None:
             c = self.model.config
@@ -64,7 +71,7 @@ class Translator:
         self.vocoder: Optional[Vocoder] = None
         if vocoder_name_or_card is not None and output_modality != Modality.TEXT:
             self.vocoder = vocoder_name_or_card if isinstance(vocoder_name_or_card, Vocoder) else \
-                load_vocoder_model(vocoder_name_or_card, device=self.device, dtype=dtype)
+                load_vocoder_model(vocoder_name_or_card, device=self.device, dtype=dtype, synthetic=bool(model_kw.get("synthetic", False)))
             self.vocoder.eval()
 
     # -- fbank + collate (translator.py:135-146): both run on device here ---------------------------------------

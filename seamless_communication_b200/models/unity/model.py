@@ -9,6 +9,7 @@ from torch import Tensor
 
 from ... import config as cfgmod
 from ... import synthetic
+from ... import synthetic as synthetic_mod
 from ...engine import UnitYEngine
 from ...nn import PaddingMask, SequenceModelOutput
 from ...ops import Seq
@@ -100,20 +101,39 @@ class UnitYModel:
 
 
 def load_unity_model(name_or_arch: str, device="cuda", dtype=torch.float16, state_dict: Optional[Dict[str, Tensor]] = None,
-                     tokenizers=None, with_t2u: bool = True, seed: int = 0, **synth_kw) -> UnitYModel:
-    """Resolves an asset-card name to its architecture (reference: models/unity/loader.py:395-402) and builds the
-    engine.  Checkpoint URLs are unreachable offline, so unless a `state_dict` in the reference's key naming is given,
-    seeded random-init weights of the named architecture are used (synthetic.make_unity_state_dict)."""
+                     tokenizers=None, with_t2u: bool = True, seed: int = 0, checkpoint=None, synthetic: bool = False,
+                     **synth_kw) -> UnitYModel:
+    """Resolves an asset-card name to its architecture (reference: models/unity/loader.py:395-402) and builds the engine.
+    Weights come from, in this order:
+      * `state_dict` - parameters in the reference's fairseq2 naming;
+      * `checkpoint` - a path or a loaded {"model": ...} mapping in the ORIGINAL fairseq naming (or fairseq2 naming),
+        converted by models/checkpoint.py (the reference's convert_unity_checkpoint, loader.py:27-389);
+      * `synthetic=True` - seeded random-init weights of the named architecture (synthetic.make_unity_state_dict;
+        `seed` and further keywords go there).  Checkpoint URLs are unreachable offline, so tests and benchmarks use this.
+    Without any of them a RuntimeError is raised: the reference would download the card's checkpoint, and silently
+    answering with random weights instead would return garbage translations."""
     arch = cfgmod.MODEL_CARDS.get(name_or_arch, name_or_arch)
     if arch not in cfgmod.UNITY_ARCHS:
         raise ValueError(f"unknown model card / architecture '{name_or_arch}'")
     if dtype != torch.float16:
         raise ValueError("the sm_100a kernels compute in fp16 with fp32 accumulation; pass dtype=torch.float16")
     cfg = cfgmod.UNITY_ARCHS[arch]()
+    if tokenizers is None:
+        if not synthetic:
+            raise RuntimeError("no tokenizers given: pass tokenizers=(text_tokenizer, char_tokenizer) matching the weights "
+                               "(the SentencePiece models of the asset card are not reachable offline), or synthetic=True")
+        tokenizers = synthetic_mod.make_tokenizers(cfg)
+    if state_dict is None and checkpoint is not None:
+        from ..checkpoint import convert_unity_checkpoint, load_checkpoint_file
+        ck = load_checkpoint_file(checkpoint) if isinstance(checkpoint, str) else checkpoint
+        ctok = tokenizers[1]
+        pieces = [ctok.model.index_to_token(i) for i in range(ctok.model.vocabulary_size)]
+        state_dict = convert_unity_checkpoint(ck, char_pieces=pieces, nllb_vocab=cfg.text_vocab)["model"]
     if state_dict is None:
-        state_dict = synthetic.make_unity_state_dict(cfg, seed=seed, with_t2u=with_t2u, **synth_kw)
+        if not synthetic:
+            raise RuntimeError(f"no weights for '{name_or_arch}': pass state_dict=..., checkpoint=... (fairseq or fairseq2 naming) "
+                               "or synthetic=True for seeded random-init weights; checkpoints cannot be downloaded here")
+        state_dict = synthetic_mod.make_unity_state_dict(cfg, seed=seed, with_t2u=with_t2u, **synth_kw)
     elif not with_t2u:
         state_dict = {k: v for k, v in state_dict.items() if not k.startswith("t2u_model.")}
-    if tokenizers is None:
-        tokenizers = synthetic.make_tokenizers(cfg)
     return UnitYModel(cfg, UnitYEngine(cfg, state_dict, tokenizers, device=device))

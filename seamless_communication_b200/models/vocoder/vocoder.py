@@ -7,7 +7,7 @@ import torch
 from torch import Tensor
 
 from ... import config as cfgmod
-from ... import synthetic
+from ... import synthetic as synthetic_mod
 from ...engine import VocoderEngine
 
 
@@ -42,11 +42,21 @@ class Vocoder:
     __call__ = forward
 
 
-def load_vocoder_model(name_or_arch: str, device="cuda", dtype=torch.float16, state_dict=None, seed: int = 1) -> Vocoder:
+def load_vocoder_model(name_or_arch: str, device="cuda", dtype=torch.float16, state_dict=None, seed: int = 1, checkpoint=None,
+                       synthetic: bool = False) -> Vocoder:
+    """Weights: `state_dict` ("code_generator.*" keys), or `checkpoint` (path / mapping, {"generator": ...} of the original
+    release or {"model": ...}; models/checkpoint.py), or `synthetic=True` for seeded random-init weights.  Without any of
+    them a RuntimeError is raised instead of silently vocoding with random weights."""
     arch = cfgmod.VOCODER_CARDS.get(name_or_arch, name_or_arch)
     if arch not in cfgmod.VOCODER_ARCHS:
         raise ValueError(f"unknown vocoder card / architecture '{name_or_arch}'")
     cfg = cfgmod.VOCODER_ARCHS[arch]()
+    if state_dict is None and checkpoint is not None:
+        from ..checkpoint import convert_vocoder_checkpoint, load_checkpoint_file
+        ck = load_checkpoint_file(checkpoint) if isinstance(checkpoint, str) else checkpoint
+        state_dict = convert_vocoder_checkpoint(ck)["model"]
     if state_dict is None:
-        state_dict = synthetic.make_vocoder_state_dict(cfg, seed=seed)
+        if not synthetic:
+            raise RuntimeError(f"no weights for vocoder '{name_or_arch}': pass state_dict=..., checkpoint=... or synthetic=True")
+        state_dict = synthetic_mod.make_vocoder_state_dict(cfg, seed=seed)
     return Vocoder(VocoderEngine(cfg, state_dict, device=device), cfgmod.vocoder_lang_spkr_idx_map())

@@ -46,7 +46,7 @@ def tiny():
 @pytest.fixture(scope="module")
 def small():
     from seamless_communication_b200.models.unity import load_unity_model
-    return load_unity_model("small_v2", seed=7, dec_gain=4.0)
+    return load_unity_model("small_v2", synthetic=True, seed=7, dec_gain=4.0)
 
 
 # ------------------------------------------------------------------------------------------------ sb_gemm

@@ -302,3 +302,43 @@ def test_scatter_gather_world_size_2_gloo(tmp_path):
                               text=True) for r in range(2)]
     outs = [p.communicate(timeout=120)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
+
+
+# ------------------------------------------------------------------------------------------------ checkpoint ingestion (8f.3)
+def test_checkpoint_conversion_matches_reference_functions():
+    """models/checkpoint.py against the mapping produced by EXECUTING the reference's own _fairseq_key_map /
+    convert_unity_checkpoint / _get_char_index_mapping / convert_vocoder_checkpoint (tests/golden/make_golden_keymap.py):
+    every example key (one per rule of the reference's table) is renamed identically, the converted state dict has the same
+    keys, and the rewritten tensors (control-symbol row permutation, NLLB dummy row, tied tables, character permutation)
+    are identical."""
+    import json
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import make_golden_keymap as mk
+    from seamless_communication_b200.models import checkpoint as ck
+    fx = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "unity_keymap.json")))
+    assert len(fx["patterns"]) >= 90
+    for old, new in fx["rename"].items():
+        if new is not None:
+            assert ck.rename_key(old) == new, (old, new, ck.rename_key(old))
+    sd = mk.make_inputs({p: None for p in fx["patterns"]})
+    out = ck.convert_unity_checkpoint({"model": sd}, char_pieces=fx["char_pieces"])["model"]
+    assert sorted(out.keys()) == fx["output_keys"]
+    for k, c in fx["checksums"].items():
+        assert mk.checksum(out[k]) == c, k
+    assert out["text_decoder_frontend.embed.weight"] is out["final_proj.weight"]          # one tied table
+    assert out["t2u_model.decoder_frontend.embed.weight"] is out["t2u_model.final_proj.weight"]
+    assert ck.char_index_mapping(fx["char_pieces"]) == fx["char_index_mapping"]
+    assert sorted(ck.convert_vocoder_checkpoint({"generator": {"conv_pre.weight_g": 1, "ups.0.bias": 2}})["model"]) == fx["vocoder_keys"]
+    # a checkpoint already in fairseq2 naming passes through
+    done = {"model": {"speech_encoder.inner.layers.0.self_attn_layer_norm.weight": torch.zeros(1)}}
+    assert ck.convert_unity_checkpoint(done)["model"] is done["model"]
+
+
+def test_model_loaders_refuse_to_invent_weights():
+    from seamless_communication_b200.models.unity import load_unity_model
+    from seamless_communication_b200.models.vocoder import load_vocoder_model
+    with pytest.raises(RuntimeError, match="synthetic=True"):
+        load_unity_model("seamlessM4T_v2_large", device="cpu")
+    with pytest.raises(RuntimeError, match="synthetic=True"):
+        load_vocoder_model("vocoder_v2", device="cpu")

@@ -36,7 +36,7 @@ def main():
         sd = S.make_unity_state_dict(cfg, seed=0, dec_gain=4.0)
         model = load_unity_model("seamlessM4T_v2_large", device="cuda", state_dict=sd, tokenizers=S.make_tokenizers(cfg))
     else:
-        model = load_unity_model("small_v2", seed=7, dec_gain=4.0)
+        model = load_unity_model("small_v2", synthetic=True, seed=7, dec_gain=4.0)
         cfg = model.engine.cfg
     eng = model.engine
     print(f"model built in {time.time() - t0:.1f}s", flush=True)
