@@ -20,6 +20,10 @@ extern "C" ggml_tensor* StandardTransformerDecoder_forward(fairseq2_model& model
                                                            ggml_tensor* padding_mask, ggml_tensor* encoder_output,
                                                            ggml_tensor* encoder_padding_mask);
 
+extern "C" ggml_tensor* ConvModule_forward(fairseq2_model& model, const std::string& prefix, ggml_tensor* seqs);
+extern "C" ggml_tensor* StandardConformerEncoderLayer_forward(fairseq2_model& model, const std::string& prefix, ggml_tensor* seqs,
+                                                              ggml_tensor* padding_mask);
+
 namespace {
 
 std::int64_t double_bits(double v) {
@@ -167,6 +171,31 @@ int fs2ref_encoder(int n_tensors, const char** names, const float** data, const 
   ggml_tensor* seqs = ggml_new_tensor_3d(ctx, GGML_TYPE_F32, model_dim, seq_len, 1);
   std::memcpy(seqs->data, x, ggml_nbytes(seqs));
   ggml_tensor* y = StandardTransformerEncoder_forward(model, prefix, seqs, nullptr);
+  ggml_cgraph* gf = ggml_new_graph(ctx);
+  ggml_build_forward_expand(gf, y);
+  ggml_graph_compute_with_ctx(ctx, gf, 1);
+  std::memcpy(out, y->data, ggml_nbytes(y));
+  ggml_free(ctx);
+  ggml_free(wctx);
+  return 0;
+}
+
+// The Conformer pieces of the mirror (w2v-BERT v1 variant): mode 0 = ConvModule_forward(prefix + ".conv")
+// (fairseq2.cpp:698-731: LayerNorm, pointwise conv, GLU, depthwise conv, BatchNorm, SiLU, pointwise conv, + residual),
+// mode 1 = StandardConformerEncoderLayer_forward(prefix) (fairseq2.cpp:733-756: the whole block, 16 heads hard-coded,
+// relative positions from the `speech_encoder.pos_enc` table).  x / out: [S][model_dim].
+int fs2ref_conformer(int n_tensors, const char** names, const float** data, const std::int64_t* d0, const std::int64_t* d1,
+                     int n_layernorm, const char** layernorm_names, double ln_eps, const char* prefix, int mode, const float* x,
+                     int seq_len, int model_dim, float* out) {
+  fairseq2_model model;
+  ggml_context* wctx = build_model(model, n_tensors, names, data, d0, d1, 0, nullptr, n_layernorm, layernorm_names, ln_eps, 0, nullptr,
+                                  16, 0, nullptr, 1);
+  ggml_context* ctx = make_ctx(512u << 20);
+  model.ctx = ctx;
+  ggml_tensor* seqs = ggml_new_tensor_2d(ctx, GGML_TYPE_F32, model_dim, seq_len);
+  std::memcpy(seqs->data, x, ggml_nbytes(seqs));
+  ggml_tensor* y = mode == 0 ? ConvModule_forward(model, std::string(prefix) + ".conv", seqs)
+                             : StandardConformerEncoderLayer_forward(model, prefix, seqs, nullptr);
   ggml_cgraph* gf = ggml_new_graph(ctx);
   ggml_build_forward_expand(gf, y);
   ggml_graph_compute_with_ctx(ctx, gf, 1);

@@ -201,3 +201,34 @@ def test_beam_search_mechanics_match_reference_cpp():
             assert abs(score - w["score"]) < 3e-3, (sc["name"], score, w["score"])
         n_hyps += len(want)
     assert n_hyps >= 30
+
+
+def test_conformer_block_matches_reference_cpp():
+    """The Conformer block of the oracle against the reference's compiled C++ `ConvModule_forward` and
+    `StandardConformerEncoderLayer_forward` (fairseq2.cpp:698-756; fixture tests/golden/make_golden_conformer.py).  The
+    mirror implements the w2v-BERT v1 block, which the oracle restates behind variant="v1"; the code path is shared with
+    the v2 block of the S2ST path except for the attention flavour, the depthwise padding side and BatchNorm vs LayerNorm,
+    so this pins block order, the 1/2 FFN scaling, every LayerNorm position, the GLU halves, the depthwise weight layout
+    and the bias-free pointwise convolutions.  Tolerance 2e-3: ggml evaluates SiLU / exp through fp16 tables."""
+    import sys
+    sys.path.insert(0, G)
+    import make_golden_conformer as mc
+    from seamless_communication_b200 import config as C
+    d = np.load(os.path.join(G, "conformer_v1_ref.npz"))
+    cfg = C.tiny_v2().to_dict()
+    cfg.update(model_dim=mc.M, num_heads=mc.H, enc_ffn_dim=mc.FFN, dw_kernel=mc.K, enc_layers=1)
+    for seed in (1, 2, 3):
+        sd = mc.oracle_state_dict(mc.make_state_dict(seed))
+        uo = UnityOracle(cfg, sd, None)
+        x = torch.from_numpy(d[f"x_{seed}"])[None]
+        conv = x + uo.conformer_conv(uo.ln(x, mc.P + ".conv_layer_norm"), mc.P + ".conv", None, variant="v1")
+        assert (conv[0] - torch.from_numpy(d[f"conv_{seed}"])).abs().max() < 2e-3
+        lay = uo.conformer_layer(x, 0, None, variant="v1", pos_enc=sd["speech_encoder.pos_enc"])
+        assert (lay[0] - torch.from_numpy(d[f"layer_{seed}"])).abs().max() < 2e-3
+        # the v2 deltas are local: causal padding = the same depthwise conv on a shifted window ...
+        k = mc.K
+        g = torch.randn(1, mc.M, 20, generator=torch.Generator().manual_seed(seed))
+        w = sd[mc.P + ".conv.depthwise_conv.weight"]
+        sym = torch.nn.functional.conv1d(torch.nn.functional.pad(g, (k // 2, k // 2)), w, groups=mc.M)
+        cau = torch.nn.functional.conv1d(torch.nn.functional.pad(g, (k - 1, 0)), w, groups=mc.M)
+        assert torch.allclose(cau[..., k // 2:], sym[..., :-(k // 2)], atol=1e-6)

@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--arch", default="base_v2")
     ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--skip-chain", action="store_true")
+    ap.add_argument("--skip-fused", action="store_true")
     ap.add_argument("--flags", default="", help="comma list of SB_DS_FLAGS values to time (fused path only)")
     ap.add_argument("--groups", default="", help="comma list of SB_DS_GROUPS values")
     ap.add_argument("--env", default="", help="semicolon list of env settings to time, e.g. 'SB_DS_PREFETCH=1;SB_DS_STAGES=2,SB_DS_PREFETCH=1'")
@@ -45,7 +46,7 @@ def main():
     e = Seq(B, S_enc, M, buf=torch.randn(B * S_enc, M, device="cuda").half())
     prefix = [cfg.text_eos, eng.text_tokenizer.lang_index("spa")]
     res = {}
-    for fused in ([True] if a.skip_chain else [False, True]):
+    for fused in ([True] if a.skip_chain else [False] if a.skip_fused else [False, True]):
         eng.decode_fused = fused
         for rep in range(a.reps + 1):
             torch.cuda.synchronize()
