@@ -18,6 +18,8 @@ random-init weights of the named architecture (no checkpoints are reachable offl
                  offline) on a bounded sample, on this box's host cores; knf (the reference's own C++ fbank) timed apart
   --impl reference : times that CPU path as the reference arm (batch 4, 1 warm-up + K timed runs).
   --config s2tt    : BASELINE configs[1] (8 x 10 s, encoder + text decoder only).
+  --config stream  : BASELINE configs[4] (SeamlessStreaming EMMA S2ST, one 30 s synthetic stream in 320 ms segments): compute
+                     latency per source segment and the real-time factor.
 """
 import argparse
 import ctypes
@@ -44,6 +46,9 @@ CONFIGS = {
                  workload="S2TT seamlessM4T_v2_large, batch 8x10s synthetic 16 kHz per GPU, beam 5, hard_max_seq_len 102 "
                           "(Conformer encoder + text decoder only) [BASELINE configs[1]]"),
 }
+STREAM_WORKLOAD = ("SeamlessStreaming S2ST (EMMA monotonic text decoder dense_1b + seamlessM4T_v2_large encoder / NAR T2U + "
+                   "vocoder_v2), one 30 s synthetic 16 kHz stream fed in 320 ms segments, reference evaluation defaults "
+                   "(cli/streaming/evaluate.py:55-66) [BASELINE configs[4]]")
 # algorithmic work per 10 s utterance at L=102, U=495 (SURVEY 8d / BASELINE.md 2)
 GFLOP_PER_UTT = {"encoder": 618.9, "t2u": 155.0, "vocoder": 165.0}
 FBANK_BYTES_PER_UTT = 0.80e6
@@ -341,13 +346,49 @@ def parity_block(tr, ref, waves_dev, task):
     return out
 
 
+def run_stream(args, device):
+    """BASELINE configs[4]: per-segment compute latency and RTF of the streaming chain (one stream, as the reference runs it)."""
+    from seamless_communication_b200 import config as C, synthetic as S
+    from seamless_communication_b200.models.monotonic_decoder import load_monotonic_decoder_model
+    from seamless_communication_b200.streaming.pipeline import StreamingS2ST
+
+    tr = build_models(device)
+    cfg = C.base_v2()
+    toks = (tr.model.engine.text_tokenizer, tr.model.engine.char_tokenizer)
+    mono = load_monotonic_decoder_model("base_v2", device=device, state_dict=S.make_monotonic_state_dict(cfg, seed=2), tokenizers=toks)
+    wave = torch.cat([w for w in S.make_waveforms(3, SAMPLES, seed=4321)])  # 30 s
+    results = []
+    for rep in range(max(1, args.warmup) + max(1, min(args.steps, 3))):
+        st = StreamingS2ST(tr.model, mono, tr.vocoder, TGT_LANG)
+        torch.cuda.synchronize()
+        ids, chunks = st.run(wave)
+        results.append(st)
+    timed = results[max(1, args.warmup):]
+    lat = sorted(x for st in timed for x in st.latencies_ms)
+    total_ms = statistics.mean(sum(st.latencies_ms) for st in timed)
+    st = timed[-1]
+    audio_s = wave.numel() / 16000.0
+    q = lambda p: lat[min(len(lat) - 1, int(p * len(lat)))]  # noqa: E731
+    line = {"metric": "streaming_s2st_rtf", "value": total_ms * 1e-3 / audio_s, "unit": "s compute / s audio", "n_gpus": 1,
+            "steps": len(timed), "warmup": max(1, args.warmup), "ms_per_step": total_ms, "higher_is_better": False, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+            "config": {"workload": STREAM_WORKLOAD, "segments": len(st.latencies_ms), "segment_ms": 320},
+            "latency_ms_per_segment": {"mean": statistics.mean(lat), "p50": q(0.5), "p95": q(0.95), "max": lat[-1]},
+            "wall_s_per_stream": st.wall_s, "text_tokens": len(st.text_ids),
+            "output_audio_s": sum(c.numel() for c in chunks) / 16000.0,
+            "source_state_builds": getattr(mono, "source_state_builds", None),
+            "e2e": {"value": st.wall_s / audio_s, "unit": "s wall / s audio", "h2d_bytes_per_step": wave.numel() * 4,
+                    "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--config", default="s2st", choices=sorted(CONFIGS))
+    ap.add_argument("--config", default="s2st", choices=sorted(CONFIGS) + ["stream"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-only", action="store_true", help="one device-resident step only (for ncu launch lists)")
     args = ap.parse_args()
@@ -355,7 +396,16 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
+        if args.config == "stream":
+            print(json.dumps({"impl": "reference", "unavailable": "the streaming agents need SimulEval + fairseq2 (absent offline); "
+                                                                   "no CPU port of the streaming chain exists"}))
+            return
         run_reference(args, rank)
+        return
+    if args.config == "stream":
+        if rank == 0:
+            torch.cuda.set_device(local)
+            run_stream(args, torch.device("cuda", local))
         return
     import torch.distributed as dist
 

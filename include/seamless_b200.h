@@ -76,6 +76,8 @@ typedef struct {
   const int32_t* seq_lens; /* per-sequence valid lengths or NULL */
   const void* prefetch;    /* optional: a device range (e.g. the next layer's weights) to pull into L2 while this GEMM runs */
   int64_t prefetch_bytes;
+  float* tile_stats;       /* optional fp32 [ceil(n/128)][m][2]: per output row and 128-column tile (max, sum exp(x - max)) of
+                              the stored values - log-softmax statistics fused into the projection (sb_logits_topk_tiles) */
 } sb_gemm_t;
 
 int sb_gemm(const sb_gemm_t* g, sb_stream_t stream);
@@ -176,6 +178,14 @@ int sb_decode_cross_attn(const void* q, const float* q_partials, int32_t splits,
 int sb_logits_topk(const float* logits, int64_t ld, int32_t rows, int32_t vocab, int32_t pad_idx, int32_t eos_idx,
                    int32_t unk_idx, float unk_penalty, int32_t K, float* cand_val, int32_t* cand_idx, float* eos_lprob,
                    sb_stream_t stream);
+
+/* Same contract as sb_logits_topk, for logits written by sb_gemm with `tile_stats`: the log-sum-exp comes from the tile
+ * statistics and only the tiles whose maximum reaches the (K+2)-th largest tile maximum are read back (a lower bound of the
+ * K-th best candidate even if PAD and UNK head two of them), i.e. ~K x 512 B per row instead of two passes over the row.
+ * Replaces log_softmax + topk over the vocabulary (fairseq2.cpp:1463-1516) without the 164 MB round trips per step. */
+int sb_logits_topk_tiles(const float* logits, int64_t ld, const float* tile_stats, int32_t rows, int32_t vocab, int32_t pad_idx,
+                         int32_t eos_idx, int32_t unk_idx, float unk_penalty, int32_t K, float* cand_val, int32_t* cand_idx,
+                         float* eos_lprob, sb_stream_t stream);
 
 /* one beam-search step for every sentence (BeamSearchSeq2SeqGenerator step, mirrored fairseq2.cpp:1463-1594).
  * State (all device, int32/fp32):

@@ -23,7 +23,7 @@ class GemmDesc(C.Structure):
         ("alpha", f32), ("gamma", f32), ("res1", c_p), ("res1_ld", i64), ("res2", c_p), ("res2_ld", i64),
         ("out", c_p), ("out_ld", i64), ("out_f32", i32), ("out2", c_p), ("out2_ld", i64), ("out2_slope", f32),
         ("out_row0", i64), ("seq_rows", i32), ("seq_halo", i32), ("seq_len", i32), ("seq_lens", c_p),
-        ("prefetch", c_p), ("prefetch_bytes", i64),
+        ("prefetch", c_p), ("prefetch_bytes", i64), ("tile_stats", c_p),
     ]
 
 
@@ -103,6 +103,7 @@ PROTOTYPES = {
     "sb_decode_self_attn": [c_p, c_p, i32, i64, c_p, c_p, c_p, c_p, i32, c_p, i32, c_p, i32, i32, c_p],
     "sb_decode_cross_attn": [c_p, c_p, i32, i64, c_p, c_p, c_p, i64, c_p, i32, c_p, i32, i32, i32, c_p],
     "sb_logits_topk": [c_p, i64, i32, i32, i32, i32, i32, f32, i32, c_p, c_p, c_p, c_p],
+    "sb_logits_topk_tiles": [c_p, i64, c_p, i32, i32, i32, i32, i32, f32, i32, c_p, c_p, c_p, c_p],
     "sb_beam_step": [C.POINTER(BeamDesc), c_p],
     "sb_kv_heads_major": [c_p, i64, i32, i32, i32, c_p, c_p, c_p],
     "sb_decoder_plan_query": [i32, i32, i32, i32, i32, i32, C.POINTER(DecoderPlanInfo)],

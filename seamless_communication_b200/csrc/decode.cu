@@ -6,6 +6,8 @@
 // whole KV cache per step (reorder_kv_cache, fairseq2.cpp:170-198).  Here the search state lives in device memory,
 // no step synchronises with the host, and beam reordering is an ancestor-index table: row r at position t reads
 // cache slot anc[r][t]; K/V are written once and never moved.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace sb {
@@ -122,10 +124,30 @@ __device__ __forceinline__ void attend_one(const elem_t* __restrict__ qp, int nk
 // reduction pass between the skinny qkv GEMM and the attention.
 __device__ __forceinline__ void gather_head_vec(const float* __restrict__ part, int splits, long long slice_rows, long long ld,
                                                 const float* __restrict__ bias, long long row, int col0, elem_t* dst) {
+  // All slices are requested before the first one is used (a plain loop serialises one L2 round trip per slice: with 4-8
+  // slices that was most of the attention kernels' time, profiles/r02_notes.md).
   const int lane = threadIdx.x & 31;
   float2 acc = *reinterpret_cast<const float2*>(bias + col0 + 2 * lane);
-  for (int z = 0; z < splits; ++z) {
-    const float2 p = *reinterpret_cast<const float2*>(part + ((long long)z * slice_rows + row) * ld + col0 + 2 * lane);
+  const float* pp = part + row * ld + col0 + 2 * lane;
+  const long long zs = slice_rows * ld;
+  int z = 0;
+  for (; z + 8 <= splits; z += 8) {
+    float2 p[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) p[u] = *reinterpret_cast<const float2*>(pp + (z + u) * zs);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { acc.x += p[u].x; acc.y += p[u].y; }
+  }
+  if (z + 4 <= splits) {
+    float2 p[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) p[u] = *reinterpret_cast<const float2*>(pp + (z + u) * zs);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { acc.x += p[u].x; acc.y += p[u].y; }
+    z += 4;
+  }
+  for (; z < splits; ++z) {
+    const float2 p = *reinterpret_cast<const float2*>(pp + z * zs);
     acc.x += p.x; acc.y += p.y;
   }
   reinterpret_cast<__half2*>(dst)[lane] = __floats2half2_rn(acc.x, acc.y);
@@ -206,6 +228,97 @@ __global__ void __launch_bounds__(128) decode_cross_attn_kernel(const elem_t* __
     qp = s_q[warp];
   }
   attend_one(qp, len, kptr, vptr, sc, out + (long long)r * dim + h * HD);
+}
+
+// Cross-attention of ALL hypotheses of one sentence in one CTA (grid: sentence x head, one warp per hypothesis).  The beams
+// of a sentence attend the same encoder keys: the CTA stages K and V of its (sentence, head) in shared memory once instead
+// of every (row, head) warp streaming them from L2 (160 rows x 16 heads x 63 keys x 256 B = 41 MB per layer and step against
+// 8 MB unique; measured 10.0 us per launch for the per-row kernel).  Scores -> probabilities (shared memory) -> values:
+// no dependent global round trip after the staging.  Lane = (key group kg, dim chunk dc) as in attend_one.
+__global__ void __launch_bounds__(256) decode_cross_attn_shared_kernel(const float* __restrict__ part, int splits, long long slice_rows,
+                                                                       const float* __restrict__ bias, const elem_t* __restrict__ k,
+                                                                       const elem_t* __restrict__ v, long long kv_ld,
+                                                                       const int* __restrict__ enc_lens, int s_enc,
+                                                                       elem_t* __restrict__ out, int beam, int heads) {
+  extern __shared__ __align__(16) unsigned char cs_smem[];
+  pdl_sync();
+  const int b = blockIdx.x, h = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, kg = lane >> 3, dc = lane & 7;
+  const int dim = heads * HD;
+  const int len = enc_lens ? min(enc_lens[b], s_enc) : s_enc;
+  elem_t* ks = reinterpret_cast<elem_t*>(cs_smem);
+  elem_t* vs = ks + (size_t)s_enc * HD;
+  float* ps = reinterpret_cast<float*>(vs + (size_t)s_enc * HD) + warp * s_enc;
+  elem_t* qs = reinterpret_cast<elem_t*>(reinterpret_cast<float*>(vs + (size_t)s_enc * HD) + (blockDim.x >> 5) * s_enc) + warp * HD;
+  const elem_t* kb = k + (long long)b * s_enc * kv_ld + h * HD;
+  const elem_t* vb = v + (long long)b * s_enc * kv_ld + h * HD;
+  for (int i = threadIdx.x; i < len * 8; i += blockDim.x) {
+    const int t = i >> 3, c = i & 7;
+    reinterpret_cast<uint4*>(ks)[i] = *reinterpret_cast<const uint4*>(kb + (long long)t * kv_ld + c * 8);
+    reinterpret_cast<uint4*>(vs)[i] = *reinterpret_cast<const uint4*>(vb + (long long)t * kv_ld + c * 8);
+  }
+  const long long r = (long long)b * beam + warp;
+  if (warp < beam) gather_head_vec(part, splits, slice_rows, dim, bias, r, h * HD, qs);
+  __syncthreads();
+  if (warp >= beam) return;
+  float q[8];
+  {
+    const uint4 u = *reinterpret_cast<const uint4*>(qs + dc * 8);
+    const __half2* hh = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(hh[e]); q[2 * e] = f.x; q[2 * e + 1] = f.y; }
+  }
+  float mx = -INFINITY;
+  for (int t0 = 0; t0 < len; t0 += 4) {  // warp-uniform trip count
+    const int t = t0 + kg;
+    const bool ok = t < len;
+    const uint4 u = ok ? *reinterpret_cast<const uint4*>(ks + (size_t)t * HD + dc * 8) : make_uint4(0, 0, 0, 0);
+    const __half2* hh = reinterpret_cast<const __half2*>(&u);
+    float a = 0.f;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(hh[e]); a += q[2 * e] * f.x + q[2 * e + 1] * f.y; }
+    a += __shfl_xor_sync(0xffffffffu, a, 1);
+    a += __shfl_xor_sync(0xffffffffu, a, 2);
+    a += __shfl_xor_sync(0xffffffffu, a, 4);
+    a *= 0.125f;
+    if (ok) {
+      if (dc == 0) ps[t] = a;
+      mx = fmaxf(mx, a);
+    }
+  }
+  mx = warp_max(mx);
+  __syncwarp();
+  float sum = 0.f;
+  for (int t = lane; t < len; t += 32) {
+    const float p = __expf(ps[t] - mx);
+    ps[t] = p;
+    sum += p;
+  }
+  sum = warp_sum(sum);
+  __syncwarp();
+  float o[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) o[e] = 0.f;
+  for (int t = kg; t < len; t += 4) {
+    const float p = ps[t];
+    const uint4 u = *reinterpret_cast<const uint4*>(vs + (size_t)t * HD + dc * 8);
+    const __half2* hh = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(hh[e]); o[2 * e] += p * f.x; o[2 * e + 1] += p * f.y; }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    o[e] += __shfl_xor_sync(0xffffffffu, o[e], 8);
+    o[e] += __shfl_xor_sync(0xffffffffu, o[e], 16);
+  }
+  if (kg == 0) {
+    const float inv = sum > 0.f ? 1.f / sum : 0.f;
+    uint4 w;
+    __half2* hh = reinterpret_cast<__half2*>(&w);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) hh[e] = __floats2half2_rn(o[2 * e] * inv, o[2 * e + 1] * inv);
+    *reinterpret_cast<uint4*>(out + r * dim + h * HD + dc * 8) = w;
+  }
 }
 
 // ------------------------------------------------------------------------------------------- log-softmax stats + top-K
@@ -320,6 +433,145 @@ __global__ void __launch_bounds__(TK_THREADS) logits_topk_kernel(const float* __
   __syncthreads();
   // ---- top-K of the candidate list, one warp
   if (warp == 0) {
+    const int n = min(s_count, TK_CAP);
+    for (int round = 0; round < K; ++round) {
+      float bv = -INFINITY; int bi = 0x7fffffff, bs = -1;
+      for (int j = lane; j < n; j += 32) {
+        const float v = s_cv[j]; const int id = s_ci[j];
+        if (v > bv || (v == bv && id < bi)) { bv = v; bi = id; bs = j; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float v2 = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int i2 = __shfl_xor_sync(0xffffffffu, bi, o);
+        const int s2 = __shfl_xor_sync(0xffffffffu, bs, o);
+        if (v2 > bv || (v2 == bv && i2 < bi)) { bv = v2; bi = i2; bs = s2; }
+      }
+      if (lane == 0) {
+        cand_val[(long long)r * K + round] = bs >= 0 ? bv - lse : -INFINITY;
+        cand_idx[(long long)r * K + round] = bs >= 0 ? bi : 0;
+        if (bs >= 0) s_cv[bs] = -INFINITY;
+      }
+      __syncwarp();
+    }
+  }
+}
+
+// Top-K from per-tile statistics (written by the projection GEMM's epilogue, sb_gemm tile_stats): one CTA per row.
+//   1. log-sum-exp of the row from the (max, sum-exp) pairs of its tiles;
+//   2. tau = (K+2)-th largest tile maximum: at least K+2 elements are >= tau, so at least K CANDIDATES are (PAD is never a
+//      candidate and the UNK penalty can push one more below);
+//   3. only the tiles whose maximum reaches tau are read back (one warp per tile, 512 B) and their elements >= tau collected;
+//   4. the same (value desc, index asc) extraction as logits_topk_kernel.
+constexpr int TKT_THREADS = 256;
+constexpr int TKT_TILE = 128;
+
+__global__ void __launch_bounds__(TKT_THREADS) logits_topk_tiles_kernel(const float* __restrict__ logits, long long ld,
+                                                                        const float2* __restrict__ stats, int rows, int vocab,
+                                                                        int pad_idx, int eos_idx, int unk_idx, float unk_penalty, int K,
+                                                                        float* __restrict__ cand_val, int* __restrict__ cand_idx,
+                                                                        float* __restrict__ eos_lprob) {
+  extern __shared__ float tk_sm[];  // tile maxima [n_tiles]
+  pdl_sync();
+  const int r = blockIdx.x;
+  const float* row = logits + (long long)r * ld;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = TKT_THREADS / 32;
+  const int n_tiles = (vocab + TKT_TILE - 1) / TKT_TILE;
+  __shared__ float s_red[TKT_THREADS / 32];
+  __shared__ int s_redi[TKT_THREADS / 32];
+  __shared__ float s_lse, s_tau;
+  __shared__ int s_count;
+  __shared__ float s_cv[TK_CAP];
+  __shared__ int s_ci[TK_CAP];
+  // ---- 1. row log-sum-exp
+  float mx = -INFINITY;
+  for (int i = threadIdx.x; i < n_tiles; i += TKT_THREADS) {
+    const float m = stats[(long long)i * rows + r].x;
+    tk_sm[i] = m;
+    mx = fmaxf(mx, m);
+  }
+  mx = warp_max(mx);
+  if (lane == 0) s_red[warp] = mx;
+  if (threadIdx.x == 0) s_count = 0;
+  __syncthreads();
+  float M = -INFINITY;
+  for (int i = 0; i < nwarp; ++i) M = fmaxf(M, s_red[i]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int i = threadIdx.x; i < n_tiles; i += TKT_THREADS) {
+    const float2 ms = stats[(long long)i * rows + r];
+    sum += ms.y * __expf(ms.x - M);
+  }
+  sum = warp_sum(sum);
+  if (lane == 0) s_red[warp] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float S = 0.f;
+    for (int i = 0; i < nwarp; ++i) S += s_red[i];
+    s_lse = M + logf(S);
+    eos_lprob[r] = row[eos_idx] - (M + logf(S));
+  }
+  __syncthreads();
+  // ---- 2. tau = (K+2)-th largest tile maximum (block-wide arg-max, K+2 rounds; the found tile is marked by negating into
+  // a side copy: tk_sm keeps the maxima, the removal is tracked in the sign-safe way below)
+  // a removed maximum is remembered as NaN in a second array to keep tk_sm intact for step 3
+  float* live = tk_sm + n_tiles;
+  for (int i = threadIdx.x; i < n_tiles; i += TKT_THREADS) live[i] = tk_sm[i];
+  __syncthreads();
+  const int rounds = min(K + 2, n_tiles);
+  float tau = -INFINITY;
+  for (int round = 0; round < rounds; ++round) {
+    float bm = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int i = threadIdx.x; i < n_tiles; i += TKT_THREADS) {
+      const float m = live[i];
+      if (m > bm || (m == bm && i < bi)) { bm = m; bi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float m2 = __shfl_xor_sync(0xffffffffu, bm, o);
+      const int i2 = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (m2 > bm || (m2 == bm && i2 < bi)) { bm = m2; bi = i2; }
+    }
+    if (lane == 0) { s_red[warp] = bm; s_redi[warp] = bi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float m = s_red[0];
+      int ix = s_redi[0];
+      for (int i = 1; i < nwarp; ++i)
+        if (s_red[i] > m || (s_red[i] == m && s_redi[i] < ix)) { m = s_red[i]; ix = s_redi[i]; }
+      if (ix < n_tiles) live[ix] = -INFINITY;
+      s_tau = m;
+    }
+    __syncthreads();
+    tau = s_tau;
+  }
+  // ---- 3. gather candidates >= tau from the tiles that can hold one
+  for (int t = warp; t < n_tiles; t += nwarp) {
+    if (!(tk_sm[t] >= tau)) continue;  // warp-uniform
+    const int i0 = t * TKT_TILE + lane * 4;
+    float xs[4];
+    if (i0 + 3 < vocab) {
+      const float4 v4 = *reinterpret_cast<const float4*>(row + i0);
+      xs[0] = v4.x; xs[1] = v4.y; xs[2] = v4.z; xs[3] = v4.w;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) xs[e] = (i0 + e < vocab) ? row[i0 + e] : -INFINITY;
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (i0 + e >= vocab) continue;
+      const float cv = tk_cand(xs[e], i0 + e, pad_idx, unk_idx, unk_penalty);
+      if (cv >= tau && cv > -INFINITY) {
+        const int slot = atomicAdd(&s_count, 1);
+        if (slot < TK_CAP) { s_cv[slot] = cv; s_ci[slot] = i0 + e; }
+      }
+    }
+  }
+  __syncthreads();
+  // ---- 4. top-K of the candidate list, one warp
+  if (warp == 0) {
+    const float lse = s_lse;
     const int n = min(s_count, TK_CAP);
     for (int round = 0; round < K; ++round) {
       float bv = -INFINITY; int bi = 0x7fffffff, bs = -1;
@@ -503,6 +755,24 @@ extern "C" int sb_decode_cross_attn(const void* q, const float* q_partials, int3
   using namespace sb;
   SB_REQUIRE((q || (q_partials && q_bias && splits >= 1)) && k && v && out && rows > 0 && heads > 0 && s_enc > 0 && beam > 0,
              SB_EINVAL, "sb_decode_cross_attn: bad args");
+  static int shared_ok = -1;
+  if (shared_ok < 0) { const char* e = getenv("SB_CROSS_ATTN_SHARED"); shared_ok = (e == nullptr || atoi(e) != 0) ? 1 : 0; }
+  if (shared_ok && q_partials != nullptr && beam <= 8 && rows % beam == 0) {
+    const int nw = beam <= 4 ? 4 : 8;
+    const size_t sm = (size_t)2 * s_enc * HD * sizeof(elem_t) + (size_t)nw * s_enc * sizeof(float) + (size_t)nw * HD * sizeof(elem_t);
+    if (sm <= 200 * 1024) {
+      static size_t configured = 0;
+      if (sm > 48 * 1024 && sm > configured) {
+        SB_CUDA_OK(cudaFuncSetAttribute(decode_cross_attn_shared_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        configured = sm;
+      }
+      SB_CUDA_OK(launch_k(decode_cross_attn_shared_kernel, dim3(rows / beam, heads), dim3(nw * 32), sm, (cudaStream_t)stream, q_partials,
+                           (int)splits, (long long)slice_rows, q_bias, (const elem_t*)k, (const elem_t*)v, (long long)kv_ld,
+                           (const int*)enc_lens, (int)s_enc, (elem_t*)out, (int)beam, (int)heads));
+      count_launch();
+      return SB_OK;
+    }
+  }
   size_t smem = (size_t)4 * s_enc * sizeof(float);
   SB_REQUIRE(smem <= 48 * 1024, SB_ENOSUP, "sb_decode_cross_attn: s_enc %d too large", s_enc);
   SB_CUDA_OK(launch_k(decode_cross_attn_kernel, dim3(rows, (heads + 3) / 4), dim3(128), smem, (cudaStream_t)stream,
@@ -522,6 +792,23 @@ extern "C" int sb_logits_topk(const float* logits, int64_t ld, int32_t rows, int
   SB_CUDA_OK(launch_k(logits_topk_kernel, dim3(rows), dim3(TK_THREADS), 0, (cudaStream_t)stream, logits, (long long)ld,
                        (int)vocab, (int)pad_idx, (int)eos_idx, (int)unk_idx, unk_penalty, (int)K, cand_val, (int*)cand_idx,
                        eos_lprob));
+  count_launch();
+  return SB_OK;
+}
+
+extern "C" int sb_logits_topk_tiles(const float* logits, int64_t ld, const float* tile_stats, int32_t rows, int32_t vocab,
+                                    int32_t pad_idx, int32_t eos_idx, int32_t unk_idx, float unk_penalty, int32_t K, float* cand_val,
+                                    int32_t* cand_idx, float* eos_lprob, sb_stream_t stream) {
+  using namespace sb;
+  SB_REQUIRE(logits && tile_stats && cand_val && cand_idx && eos_lprob && rows > 0 && vocab > 0, SB_EINVAL, "sb_logits_topk_tiles: bad args");
+  SB_REQUIRE(K > 0 && K <= TK_MAX, SB_ENOSUP, "sb_logits_topk_tiles: K=%d unsupported (<= %d)", K, TK_MAX);
+  SB_REQUIRE(ld % 4 == 0 && ((uintptr_t)logits % 16) == 0, SB_EINVAL, "sb_logits_topk_tiles: logits must be 16-byte aligned rows");
+  const int n_tiles = (vocab + TKT_TILE - 1) / TKT_TILE;
+  const size_t smem = (size_t)2 * n_tiles * sizeof(float);
+  SB_REQUIRE(smem <= 40 * 1024, SB_ENOSUP, "sb_logits_topk_tiles: vocabulary of %d too large", vocab);
+  SB_CUDA_OK(launch_k(logits_topk_tiles_kernel, dim3(rows), dim3(TKT_THREADS), smem, (cudaStream_t)stream, logits, (long long)ld,
+                       (const float2*)tile_stats, (int)rows, (int)vocab, (int)pad_idx, (int)eos_idx, (int)unk_idx, unk_penalty, (int)K,
+                       cand_val, (int*)cand_idx, eos_lprob));
   count_launch();
   return SB_OK;
 }

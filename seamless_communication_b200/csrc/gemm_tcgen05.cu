@@ -51,6 +51,7 @@ struct GemmArgs {
   int m_fast;  // skinny-M problems: blockIdx.x walks the M tiles so CTAs sharing a weight tile are co-scheduled (L2 reuse)
   int kb_per_split;  // split-K: k-blocks per blockIdx.z slice (0 = no split)
   long long slice_rows;  // split-K: slice z writes rows [z*slice_rows, z*slice_rows + m) of out
+  float2* tile_stats;    // optional [n tiles][m]: (max, sum exp(x - max)) of every output row over this CTA's BN columns
   const char* prefetch;  // weights of the kernel that follows: pulled into L2 by the idle epilogue warp during the main loop
   long long prefetch_bytes;
 };
@@ -238,6 +239,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int n_acc = total_steps < Cfg::NACC ? total_steps : Cfg::NACC;
     const bool has_res = valid && (g.res1 != nullptr || g.res2 != nullptr);
     const float post_scale = has_res ? g.gamma : g.alpha * g.gamma;
+    float st_m = -INFINITY, st_s = 0.f;  // running log-sum-exp statistics of this thread's row (tile_stats)
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       if (n0 + c0 >= g.n) break;  // warp-uniform
@@ -307,6 +309,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = valid ? v[j] * post_scale : 0.f;
+      if (g.tile_stats != nullptr) {
+        // per (row, column tile) softmax statistics of what is being stored: the consumer (sb_logits_topk_tiles) gets the
+        // row's log-sum-exp and the tiles that can hold its top-K without reading the logits back
+        float cm = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) if (j < nv && oc + j < n_out_total) cm = fmaxf(cm, v[j]);
+        if (cm > -INFINITY) {
+          const float nm = fmaxf(st_m, cm);
+          float acc = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) if (j < nv && oc + j < n_out_total) acc += __expf(v[j] - nm);
+          st_s = st_s * __expf(st_m - nm) + acc;
+          st_m = nm;
+        }
+      }
       // stores
       if (g.tma_store) {
         // stage into shared memory: 16 KB groups of [128 rows][128 B], 16-byte chunk index XOR (row & 7) (SWIZZLE_128B)
@@ -388,6 +405,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (j < nv && oc + j < n_out_total) p[j] = __float2half_rn(v[j] > 0.f ? v[j] : v[j] * g.out2_slope);
       }
     }
+    if (g.tile_stats != nullptr && row_ok) g.tile_stats[(long long)(n0 / BN) * g.m + m] = make_float2(st_m, st_s);
     if (g.tma_store) {
       // make the staged tile visible to the async proxy, then one thread issues the bulk tensor stores
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -472,6 +490,7 @@ static void fill_args(const sb_gemm_t* g, GemmArgs* a) {
   a->out2 = (elem_t*)g->out2; a->out2_ld = g->out2_ld; a->out2_slope = g->out2_slope;
   a->out_row0 = g->out_row0;
   a->seq_rows = g->seq_rows; a->seq_halo = g->seq_halo; a->seq_len = g->seq_len; a->seq_lens = g->seq_lens;
+  a->tile_stats = (float2*)g->tile_stats;
   a->prefetch = (const char*)g->prefetch; a->prefetch_bytes = g->prefetch ? g->prefetch_bytes / 4096 * 4096 : 0;
   a->tma_store = 0;
   a->kb_per_split = 0;
@@ -605,6 +624,10 @@ extern "C" int sb_gemm(const sb_gemm_t* g_in, sb_stream_t stream) {
   }
   const long long mt = (g->m + sb::BM - 1) / sb::BM;
   auto tiles = [&](int bn) { return mt * ((g->n + bn - 1) / bn); };
+  if (g->tile_stats != nullptr) {
+    SB_REQUIRE(!g->glu && g->n >= 128, SB_ENOSUP, "sb_gemm: tile_stats needs n >= 128 and no GLU");
+    return sb::launch<128>(g, st);  // the statistics are per 128-column tile (SB_STATS_TILE)
+  }
   // largest N tile that still gives every SM two CTAs; fall back to smaller tiles for skinny problems
   if (g->n >= 128 && tiles(128) >= 148) return sb::launch<128>(g, st);
   if (g->n >= 64 && tiles(64) >= 148) return sb::launch<64>(g, st);

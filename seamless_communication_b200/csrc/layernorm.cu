@@ -126,6 +126,20 @@ __global__ void __launch_bounds__(32 * LN_MAX_CHUNKS) splitk_reduce_ln_kernel(co
       acc[0] += b0.x; acc[1] += b0.y; acc[2] += b0.z; acc[3] += b0.w; acc[4] += b1.x; acc[5] += b1.y; acc[6] += b1.z; acc[7] += b1.w;
     }
     int z = 0;
+    for (; z + 8 <= splits; z += 8) {  // 16 loads in flight per lane: one round trip for up to 8 slices
+      float4 p0[8], p1[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float* pp = partials + ((long long)(z + u) * slice_rows + row) * dim + off;
+        p0[u] = *reinterpret_cast<const float4*>(pp);
+        p1[u] = *reinterpret_cast<const float4*>(pp + 4);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        acc[0] += p0[u].x; acc[1] += p0[u].y; acc[2] += p0[u].z; acc[3] += p0[u].w;
+        acc[4] += p1[u].x; acc[5] += p1[u].y; acc[6] += p1[u].z; acc[7] += p1[u].w;
+      }
+    }
     for (; z + 4 <= splits; z += 4) {
       float4 p0[4], p1[4];
 #pragma unroll

@@ -54,6 +54,7 @@ class UnitYEngine:
         self.M, self.H = cfg.model_dim, cfg.num_heads
         assert cfg.head_dim == 64, "attention kernels are specialised for head_dim 64"
         self.has_t2u = any(k.startswith("t2u_model.") for k in state_dict)
+        self.has_encoder = any(k.startswith("speech_encoder.") for k in state_dict)  # a monotonic text decoder has none
         self._pack(state_dict)
         self.pos = sinusoid_table(cfg.max_seq_len, self.M).to(self.device)
         if self.has_t2u:
@@ -72,6 +73,7 @@ class UnitYEngine:
         # (profiles/r02_notes.md).
         self.decode_fused = os.environ.get("SB_DECODER_FUSED", "0") != "0"
         self.decode_timeline = os.environ.get("SB_DS_TIMELINE", "0") != "0"
+        self.topk_tiles = os.environ.get("SB_TOPK_TILES", "1") != "0"  # top-K from the projection's per-tile statistics
 
     # ------------------------------------------------------------------------------------------ weight packing
     def _pack(self, sd):
@@ -113,9 +115,10 @@ class UnitYEngine:
             lin(name + ".output_proj")
 
         c = self.cfg
-        ln("speech_encoder_frontend.post_extract_layer_norm")
-        lin("speech_encoder_frontend.model_dim_proj")
-        for i in range(c.enc_layers):
+        if self.has_encoder:
+            ln("speech_encoder_frontend.post_extract_layer_norm")
+            lin("speech_encoder_frontend.model_dim_proj")
+        for i in range(c.enc_layers if self.has_encoder else 0):
             p = f"speech_encoder.inner.layers.{i}"
             for n in ("ffn1", "ffn2"):
                 ln(f"{p}.{n}_layer_norm"); lin(f"{p}.{n}.inner_proj"); lin(f"{p}.{n}.output_proj")
@@ -127,12 +130,13 @@ class UnitYEngine:
             ln(f"{p}.conv.layer_norm")
             conv(f"{p}.conv.pointwise_conv2")
             ln(f"{p}.layer_norm")
-        ln("speech_encoder.inner_layer_norm"); lin("speech_encoder.proj1"); lin("speech_encoder.proj2")
-        p = "speech_encoder.adaptor_layers.0"
-        ln(f"{p}.residual_layer_norm"); conv(f"{p}.residual_conv", glu=True)
-        ln(f"{p}.self_attn_layer_norm"); conv(f"{p}.self_attn_conv", glu=True)
-        mha(f"{p}.self_attn"); ln(f"{p}.ffn_layer_norm"); lin(f"{p}.ffn.inner_proj"); lin(f"{p}.ffn.output_proj")
-        ln("speech_encoder.layer_norm")
+        if self.has_encoder:
+            ln("speech_encoder.inner_layer_norm"); lin("speech_encoder.proj1"); lin("speech_encoder.proj2")
+            p = "speech_encoder.adaptor_layers.0"
+            ln(f"{p}.residual_layer_norm"); conv(f"{p}.residual_conv", glu=True)
+            ln(f"{p}.self_attn_layer_norm"); conv(f"{p}.self_attn_conv", glu=True)
+            mha(f"{p}.self_attn"); ln(f"{p}.ffn_layer_norm"); lin(f"{p}.ffn.inner_proj"); lin(f"{p}.ffn.output_proj")
+            ln("speech_encoder.layer_norm")
         w["text_embed"] = h(sd["text_decoder_frontend.embed.weight"])  # tied with final_proj (builder.py:451)
         for i in range(c.dec_layers):
             p = f"text_decoder.layers.{i}"
@@ -224,6 +228,8 @@ class UnitYEngine:
     @torch.inference_mode()
     def encode_speech(self, fbank: torch.Tensor, lens: Optional[torch.Tensor], return_inner=False):
         """fbank (B, T_fb, 80) fp16 cuda, lens (B,) int32 cuda or None -> encoder output Seq (B, S_a, M), lens."""
+        if not self.has_encoder:
+            raise RuntimeError("this engine was built without a speech encoder (text-decoder-only state dict)")
         c, M = self.cfg, self.M
         B, T_fb, Cf = fbank.shape
         s = c.fbank_stride
@@ -292,7 +298,7 @@ class UnitYEngine:
         if st.get("ds_launch") is not None:
             # embedding frontend + all decoder layers + final LayerNorm (+ hist[step] = h) in one persistent kernel
             check(lib.sb_decoder_step(C.byref(st["ds_launch"]), stream), "sb_decoder_step")
-            ops.gemm(h, w["text_embed"], c.text_vocab, None, out=st["logits"], out_f32=True)
+            ops.gemm(h, w["text_embed"], c.text_vocab, None, out=st["logits"], out_f32=True, tile_stats=st["tile_stats"])
             return
         check(lib.sb_embed_step(st["seqs"].data_ptr(), st["ML"], st["step"].data_ptr(), w["text_embed"].data_ptr(),
                                 self.pos.data_ptr(), math.sqrt(M), x.buf.data_ptr(), R, M, stream), "sb_embed_step")
@@ -337,15 +343,24 @@ class UnitYEngine:
                             skinny=sk["ffn2"])
             ops.splitk_reduce_ln(part, S_FFN, w[p + ".ffn.output_proj.b"], x, w[nxt + ".w"], w[nxt + ".b"], h)
         check(lib.sb_store_step(h.buf.data_ptr(), st["hist"].data_ptr(), st["step"].data_ptr(), R * M * 2, stream), "sb_store_step")
-        ops.gemm(h, w["text_embed"], c.text_vocab, None, out=st["logits"], out_f32=True)
+        ops.gemm(h, w["text_embed"], c.text_vocab, None, out=st["logits"], out_f32=True, tile_stats=st["tile_stats"])
+
+    def _topk(self, st, eos_idx, unk_penalty):
+        """log-softmax statistics + top-K candidates of every row (st["logits"] / st["tile_stats"] of the last projection)."""
+        lib, c = _lib.load(), self.cfg
+        if st["tile_stats"] is not None:
+            check(lib.sb_logits_topk_tiles(st["logits"].buf.data_ptr(), st["logits"].buf.stride(0), st["tile_stats"].data_ptr(), st["R"],
+                                           c.text_vocab, c.text_pad, eos_idx, c.text_unk, unk_penalty, st["K"], st["cand_val"].data_ptr(),
+                                           st["cand_idx"].data_ptr(), st["eos_lprob"].data_ptr(), ops._stream()), "sb_logits_topk_tiles")
+        else:
+            check(lib.sb_logits_topk(st["logits"].buf.data_ptr(), st["logits"].buf.stride(0), st["R"], c.text_vocab, c.text_pad,
+                                     eos_idx, c.text_unk, unk_penalty, st["K"], st["cand_val"].data_ptr(),
+                                     st["cand_idx"].data_ptr(), st["eos_lprob"].data_ptr(), ops._stream()), "sb_logits_topk")
 
     def _decoder_step_select(self, st):
         lib = _lib.load()
-        c = self.cfg
         stream = ops._stream()
-        check(lib.sb_logits_topk(st["logits"].buf.data_ptr(), st["logits"].buf.stride(0), st["R"], c.text_vocab, c.text_pad,
-                                 c.text_eos, c.text_unk, st["unk_penalty"], st["K"], st["cand_val"].data_ptr(),
-                                 st["cand_idx"].data_ptr(), st["eos_lprob"].data_ptr(), stream), "sb_logits_topk")
+        self._topk(st, self.cfg.text_eos, st["unk_penalty"])
         check(lib.sb_beam_step(C.byref(st["beam_desc"]), stream), "sb_beam_step")
         check(lib.sb_step_advance(st["step"].data_ptr(), stream), "sb_step_advance")
 
@@ -401,6 +416,9 @@ class UnitYEngine:
                                      device=dev)
         st["logits"] = Seq(1, R, c.text_vocab, dtype=torch.float32, buf=torch.empty(
             (R, (c.text_vocab + 7) // 8 * 8), dtype=torch.float32, device=dev))
+        # per (128-column tile, row) softmax statistics written by the projection's epilogue (None: two-pass top-K over the logits)
+        st["tile_stats"] = (torch.empty(((c.text_vocab + 127) // 128, R, 2), dtype=torch.float32, device=dev)
+                            if self.topk_tiles and c.text_vocab >= 128 else None)
         st["cand_val"] = torch.empty((R, K), dtype=torch.float32, device=dev)
         st["cand_idx"] = torch.empty((R, K), dtype=I32, device=dev)
         st["eos_lprob"] = torch.empty((R,), dtype=torch.float32, device=dev)
@@ -582,9 +600,7 @@ class UnitYEngine:
         `eos_idx` argument, here the next prefix token)."""
         lib, c = _lib.load(), self.cfg
         self._search_step(st, use_graph, select=False)
-        check(lib.sb_logits_topk(st["logits"].buf.data_ptr(), st["logits"].buf.stride(0), st["R"], c.text_vocab, c.text_pad,
-                                 prefix[i + 1], c.text_unk, 0.0, st["K"], st["cand_val"].data_ptr(), st["cand_idx"].data_ptr(),
-                                 st["eos_lprob"].data_ptr(), ops._stream()), "sb_logits_topk")
+        self._topk(st, prefix[i + 1], 0.0)
         st["scores"][:, i + 1] = st["scores"][:, i] + st["eos_lprob"]
         check(lib.sb_step_advance(st["step"].data_ptr(), ops._stream()), "sb_step_advance")
 

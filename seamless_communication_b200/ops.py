@@ -56,7 +56,8 @@ class Seq:
 
 def gemm(a: Seq, w: torch.Tensor, n: int, bias=None, *, taps=1, dil=1, act=ACT_NONE, slope=0.0, glu=False, alpha=1.0,
          gamma=1.0, res1: Optional[Seq] = None, res2: Optional[Seq] = None, out: Optional[Seq] = None,
-         out2: Optional[Seq] = None, out2_slope=0.0, mask=None, out_f32=False, ref=False, prefetch: Optional[torch.Tensor] = None) -> Seq:
+         out2: Optional[Seq] = None, out2_slope=0.0, mask=None, out_f32=False, ref=False, prefetch: Optional[torch.Tensor] = None,
+         tile_stats: Optional[torch.Tensor] = None) -> Seq:
     """Linear (taps=1) or 'same'-padded Conv1d (odd taps, dilation dil) over a Seq; output shares a's layout."""
     lib = _lib.load()
     halo = (taps - 1) * dil // 2
@@ -85,6 +86,8 @@ def gemm(a: Seq, w: torch.Tensor, n: int, bias=None, *, taps=1, dil=1, act=ACT_N
         d.seq_rows, d.seq_halo, d.seq_len, d.seq_lens = a.Tp, a.PH, a.T, _p(a.lens)
     if prefetch is not None:
         d.prefetch, d.prefetch_bytes = prefetch.data_ptr(), prefetch.numel() * prefetch.element_size()
+    if tile_stats is not None:
+        d.tile_stats = tile_stats.data_ptr()
     fn = lib.sb_gemm_ref if ref else lib.sb_gemm
     check(fn(C.byref(d), _stream()), "sb_gemm")
     return out

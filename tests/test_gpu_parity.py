@@ -250,6 +250,56 @@ def test_logits_topk_exact(ops):
         assert ci[r].tolist() == ti[r].tolist()
 
 
+def test_logits_topk_from_projection_tile_statistics_exact(ops):
+    """sb_gemm(tile_stats=...) + sb_logits_topk_tiles: the log-softmax statistics leave the projection's epilogue and only
+    the tiles that can hold a top-K candidate are read back.  Same answers as log_softmax + topk over the produced fp32
+    logits: values, indices (lowest index first on exact ties), the lprob of an arbitrary token; PAD excluded, UNK penalised;
+    ragged last tile; PAD / UNK / tied tokens heading the row."""
+    from seamless_communication_b200 import _lib
+    from seamless_communication_b200.ops import Seq
+    lib = _lib.load()
+    R, V, K, D = 37, 20000 + 102, 11, 256
+    torch.manual_seed(8)
+    a = Seq(1, R, D, buf=torch.randn(R, D, device=dev).half())
+    w = (torch.randn(V, D, device=dev) * 0.25).half()
+    w[0] = a.buf[3] * 0.5            # PAD would be the best token of row 3
+    w[1] = a.buf[5] * 0.5            # UNK would be the best token of row 5 (before the penalty)
+    w[700:740] = a.buf[9] * 0.4      # forty exactly tied best tokens for row 9, spanning two tiles
+    w[V - 1] = a.buf[11] * 0.5       # best token of row 11 sits in the ragged last tile
+    ld = (V + 7) // 8 * 8
+    logits = Seq(1, R, V, dtype=torch.float32, buf=torch.full((R, ld), float("nan"), device=dev))
+    stats = torch.full(((V + 127) // 128, R, 2), float("nan"), device=dev)
+    ops.gemm(a, w, V, None, out=logits, out_f32=True, tile_stats=stats)
+    lg = logits.buf[:, :V]
+    assert torch.isfinite(lg).all() and torch.isfinite(stats).all()
+    # the statistics themselves
+    tiles = lg.new_full((R, stats.shape[0] * 128), -math.inf)
+    tiles[:, :V] = lg
+    tiles = tiles.view(R, -1, 128)
+    assert torch.equal(stats[:, :, 0].t(), tiles.max(-1).values)
+    assert torch.allclose(stats[:, :, 1].t(), torch.exp(tiles - tiles.max(-1, keepdim=True).values).sum(-1), rtol=1e-5)
+    cv = torch.empty(R, K, device=dev); ci = torch.empty(R, K, dtype=torch.int32, device=dev); el = torch.empty(R, device=dev)
+    _lib.check(lib.sb_logits_topk_tiles(logits.buf.data_ptr(), ld, stats.data_ptr(), R, V, 0, 3, 1, 2.5, K, cv.data_ptr(), ci.data_ptr(),
+                                        el.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    lp = torch.log_softmax(lg, -1)
+    assert (el - lp[:, 3]).abs().max() < 1e-4
+    lp[:, 0] = -math.inf
+    lp[:, 1] -= 2.5
+    tv, ti = torch.sort(lp, dim=-1, descending=True, stable=True)  # stable: the lowest index first among exact ties
+    tv, ti = tv[:, :K], ti[:, :K]
+    assert (tv - cv).abs().max() < 1e-4
+    assert ci[9].tolist() == list(range(700, 711))     # exact ties: lowest indices win
+    assert ci[11, 0].item() == V - 1
+    assert 0 not in ci[3].tolist()                     # PAD is never a candidate
+    for r in range(R):
+        assert ci[r].tolist() == ti[r].tolist(), r
+    # and it agrees with the two-pass kernel on the same logits
+    cv2 = torch.empty_like(cv); ci2 = torch.empty_like(ci); el2 = torch.empty_like(el)
+    _lib.check(lib.sb_logits_topk(logits.buf.data_ptr(), ld, R, V, 0, 3, 1, 2.5, K, cv2.data_ptr(), ci2.data_ptr(), el2.data_ptr(),
+                                  torch.cuda.current_stream().cuda_stream))
+    assert torch.equal(ci, ci2) and (cv - cv2).abs().max() < 1e-5
+
+
 # ------------------------------------------------------------------------------------------------ encoder (a3-a6)
 def test_encoder_matches_oracle_ragged(tiny, ops):
     waves = S.make_waveforms(3, 32000)
@@ -758,3 +808,31 @@ def test_monotonic_decoder_pchoose_and_policy_match_oracle():
         if finished:
             break
     assert written == o_target and len(written) > 0
+
+
+def test_streaming_s2st_chain_runs_and_reuses_source_state(tiny):
+    """The SeamlessStreaming chain on the tiny models: feature extractor residual carry (every sample is framed exactly
+    once), the encoder re-encode, READ/WRITE policy, unit chunks and vocoder; the per-source decoder state (cross K/V,
+    key energies) is built once per encoder output, not once per token."""
+    from seamless_communication_b200.models.monotonic_decoder import load_monotonic_decoder_model
+    from seamless_communication_b200.streaming.pipeline import OnlineFeatureExtractor, StreamingS2ST
+    cfg = tiny["cfg"]
+    sd = S.make_monotonic_state_dict(cfg, seed=2)
+    mono = load_monotonic_decoder_model("tiny_v2", state_dict=sd, tokenizers=tiny["toks"])
+    wave = S.make_waveforms(1, 48000, seed=5)[0]
+    # feature extractor: streaming frames == offline frames of the same samples (no standardisation)
+    fx = OnlineFeatureExtractor(dev)
+    got = [f for s0 in range(0, 48000, 5120) if (f := fx.push(wave[s0:s0 + 5120])) is not None]
+    got = torch.cat(got).float().cpu()
+    ref = o_fbank_raw(wave)
+    assert abs(got.shape[0] - ref.shape[0]) <= 1  # 298 frames either way (the last partial window stays in the residual)
+    n = min(got.shape[0], ref.shape[0])
+    assert (got[:n] - ref[:n]).abs().max() < 2e-2
+    st = StreamingS2ST(tiny["model"], mono, tiny["voc"], "spa", min_starting_wait_w2vbert=40, min_unit_chunk_size=5, max_len_b=12)
+    ids, chunks = st.run(wave)
+    assert len(st.latencies_ms) == math.ceil(48000 / 5120)
+    assert len(ids) > 0 and all(0 <= i < cfg.text_vocab for i in ids)
+    assert len(chunks) > 0 and all(torch.isfinite(c).all() for c in chunks)
+    calls = mono.source_state_builds
+    # one build per distinct encoder output (<= number of segments), although the policy ran the decoder many more times
+    assert calls <= len(st.latencies_ms)

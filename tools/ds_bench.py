@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--skip-chain", action="store_true")
     ap.add_argument("--skip-fused", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="torch.profiler kernel table of one search (launch chain)")
     ap.add_argument("--flags", default="", help="comma list of SB_DS_FLAGS values to time (fused path only)")
     ap.add_argument("--groups", default="", help="comma list of SB_DS_GROUPS values")
     ap.add_argument("--env", default="", help="semicolon list of env settings to time, e.g. 'SB_DS_PREFETCH=1;SB_DS_STAGES=2,SB_DS_PREFETCH=1'")
@@ -45,6 +46,16 @@ def main():
     M, S_enc, B = cfg.model_dim, 63, a.batch
     e = Seq(B, S_enc, M, buf=torch.randn(B * S_enc, M, device="cuda").half())
     prefix = [cfg.text_eos, eng.text_tokenizer.lang_index("spa")]
+    if a.profile:
+        from torch.profiler import ProfilerActivity, profile
+        eng.decode_fused = False
+        eng.beam_search(e, None, prefix, beam=5, soft_max=(1, 200), hard_max=a.hard_max)
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+            eng.beam_search(e, None, prefix, beam=5, soft_max=(1, 200), hard_max=a.hard_max)
+            torch.cuda.synchronize()
+        print(prof.key_averages().table(sort_by="self_cuda_time_total", row_limit=22, max_name_column_width=70))
+        return
     res = {}
     for fused in ([True] if a.skip_chain else [False] if a.skip_fused else [False, True]):
         eng.decode_fused = fused
