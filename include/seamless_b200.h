@@ -93,6 +93,13 @@ int sb_gemm_splitk(const sb_gemm_t* g, int32_t splits, float* partials, int64_t 
  * (taps 1, m <= 160, n % 64 == 0, c_in % (64 * splits) == 0, 16-byte aligned operands). */
 int sb_gemm_skinny_supported(const sb_gemm_t* g, int32_t splits);
 int sb_gemm_skinny(const sb_gemm_t* g, int32_t splits, float* partials, int64_t slice_rows, sb_stream_t stream);
+/* The same products for at most 256 rows in TRANSPOSED form on tcgen05 (decode_gemm.cu): a 128-feature weight tile is the
+ * MMA A operand and all rows are the B operand, so a CTA reads its weights once and the activations once per k-block
+ * (the row-major kernel re-reads a 128-row activation tile for every 64 features and is L2 -> SM bound at 160 rows).
+ * partials != NULL: split-K mode, same output contract as sb_gemm_splitk (splits need not divide the k-blocks).
+ * partials == NULL (splits must be 1): out = act(a . w^T + bias) in fp16, act in {none, relu}. */
+int sb_gemm_decode_supported(const sb_gemm_t* g, int32_t splits);
+int sb_gemm_decode(const sb_gemm_t* g, int32_t splits, float* partials, int64_t slice_rows, sb_stream_t stream);
 /* consumer of the partials: x += bias + sum_z partial[z] (x fp16 [rows][dim], updated in place) and h = LayerNorm(x).
  * Fuses the reduction into the LayerNorm that follows every residual GEMM of a pre-LN decoder layer
  * (StandardTransformerDecoderLayer, fairseq2.cpp:979-1060). */

@@ -73,6 +73,10 @@ class UnitYEngine:
         # (profiles/r02_notes.md).
         self.decode_fused = os.environ.get("SB_DECODER_FUSED", "0") != "0"
         self.decode_timeline = os.environ.get("SB_DS_TIMELINE", "0") != "0"
+        # SB_DECODE_GEMM_T=1: q|k|v / FFN products of the decoder step on the transposed tcgen05 kernel (decode_gemm.cu).
+        # Opt-in: it moves 2.6x fewer bytes through L2 but measured 12.4 us per launch against 10.7 us for the row-major
+        # kernel at 2 CTAs per SM (profiles/r02_notes.md) - at these sizes the launches are bound by fixed latencies.
+        self.decode_gemm_t = os.environ.get("SB_DECODE_GEMM_T", "0") != "0"
         self.topk_tiles = os.environ.get("SB_TOPK_TILES", "1") != "0"  # top-K from the projection's per-tile statistics
 
     # ------------------------------------------------------------------------------------------ weight packing
@@ -313,7 +317,7 @@ class UnitYEngine:
             w_next = None if last else w[f"text_decoder.layers.{i + 1}.self_attn.qkv.w"]
             # qkv / q projections also run split-K; their partials are reduced (+bias) inside the attention kernels
             ops.gemm_splitk(h, w[p + ".self_attn.qkv.w"], 3 * M, S_QKV, st["part_qkv"],
-                            prefetch=w[p + ".self_attn.output_proj.w"] if pf else None, skinny=sk["qkv"])
+                            prefetch=w[p + ".self_attn.output_proj.w"] if pf else None, skinny=sk["qkv"], transposed=st["gemm_t"])
             check(lib.sb_decode_self_attn(None, st["part_qkv"].data_ptr(), S_QKV, SR, w[p + ".self_attn.qkv.b"].data_ptr(),
                                           st["kc"][i].data_ptr(), st["vc"][i].data_ptr(), st["anc"].data_ptr(), st["ML"],
                                           st["step"].data_ptr(), st["ML"], st["att"].buf.data_ptr(), R, H, stream),
@@ -333,14 +337,17 @@ class UnitYEngine:
                             prefetch=w[p + ".ffn.inner_proj.w"] if pf else None, skinny=sk["attn"])
             ops.splitk_reduce_ln(part, S_ATT, w[p + ".encoder_decoder_attn.output_proj.b"], x, w[p + ".ffn_layer_norm.w"],
                                  w[p + ".ffn_layer_norm.b"], h)
-            if sk["ffn1"]:
+            if st["gemm_t"]:
+                t = ops.gemm_decode(h, w[p + ".ffn.inner_proj.w"], c.dec_ffn_dim, w[p + ".ffn.inner_proj.b"], act=ACT_RELU,
+                                    out=st["ffn"], prefetch=w[p + ".ffn.output_proj.w"] if pf else None)
+            elif sk["ffn1"]:
                 t = ops.gemm_skinny(h, w[p + ".ffn.inner_proj.w"], c.dec_ffn_dim, w[p + ".ffn.inner_proj.b"], act=ACT_RELU,
                                     out=st["ffn"], prefetch=w[p + ".ffn.output_proj.w"] if pf else None)
             else:
                 t = self._lin(h, p + ".ffn.inner_proj", c.dec_ffn_dim, act=ACT_RELU, out=st["ffn"],
                               prefetch=w[p + ".ffn.output_proj.w"] if pf else None)
             ops.gemm_splitk(t, w[p + ".ffn.output_proj.w"], M, S_FFN, part, prefetch=w_next if pf else None,
-                            skinny=sk["ffn2"])
+                            skinny=sk["ffn2"], transposed=st["gemm_t"])
             ops.splitk_reduce_ln(part, S_FFN, w[p + ".ffn.output_proj.b"], x, w[nxt + ".w"], w[nxt + ".b"], h)
         check(lib.sb_store_step(h.buf.data_ptr(), st["hist"].data_ptr(), st["step"].data_ptr(), R * M * 2, stream), "sb_store_step")
         ops.gemm(h, w["text_embed"], c.text_vocab, None, out=st["logits"], out_f32=True, tile_stats=st["tile_stats"])
@@ -411,6 +418,13 @@ class UnitYEngine:
         while k_att % st["splits_qkv"]: st["splits_qkv"] -= 1
         while k_att % st["splits_attn"]: st["splits_attn"] -= 1
         while k_ffn % st["splits_ffn"]: st["splits_ffn"] -= 1
+        # <= 256 rows: q|k|v, FFN inner and FFN output run on the transposed tcgen05 kernel (decode_gemm.cu: the row-major
+        # kernel is L2 -> SM bound at these shapes); one (128-feature tile, K slice) unit per CTA, splits fill the machine
+        st["gemm_t"] = self.decode_gemm_t and R <= 256 and M % 64 == 0 and c.dec_ffn_dim % 64 == 0
+        if st["gemm_t"]:
+            sms = torch.cuda.get_device_properties(dev).multi_processor_count
+            st["splits_qkv"] = max(1, min(k_att // 2, sms // ((3 * M + 127) // 128)))
+            st["splits_ffn"] = max(1, min(k_ffn // 4, 16, sms // ((M + 127) // 128)))
         st["part_qkv"] = torch.empty((st["splits_qkv"] * ops.slice_rows(R), 3 * M), dtype=torch.float32, device=dev)
         st["partials"] = torch.empty((max(st["splits_attn"], st["splits_ffn"]) * ops.slice_rows(R), M), dtype=torch.float32,
                                      device=dev)

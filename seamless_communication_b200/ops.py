@@ -158,7 +158,7 @@ def slice_rows(rows: int) -> int:
 
 
 def gemm_splitk(a: Seq, w: torch.Tensor, n: int, splits: int, partials: torch.Tensor,
-                prefetch: Optional[torch.Tensor] = None, skinny=False) -> None:
+                prefetch: Optional[torch.Tensor] = None, skinny=False, transposed=False) -> None:
     """Raw fp32 partial products of a (dense) Seq against w into partials[(z*slice_rows(rows) + r), n]."""
     lib = _lib.load()
     assert a.PH == 0 and a.Tp == a.T
@@ -168,10 +168,31 @@ def gemm_splitk(a: Seq, w: torch.Tensor, n: int, splits: int, partials: torch.Te
     d.out = partials.data_ptr()  # validated as non-null; sb_gemm_splitk overrides the epilogue fields
     if prefetch is not None:
         d.prefetch, d.prefetch_bytes = prefetch.data_ptr(), prefetch.numel() * prefetch.element_size()
+    if transposed and lib.sb_gemm_decode_supported(C.byref(d), splits):
+        check(lib.sb_gemm_decode(C.byref(d), splits, partials.data_ptr(), slice_rows(a.B * a.T), _stream()), "sb_gemm_decode")
+        return
     if skinny and lib.sb_gemm_skinny_supported(C.byref(d), splits):
         check(lib.sb_gemm_skinny(C.byref(d), splits, partials.data_ptr(), slice_rows(a.B * a.T), _stream()), "sb_gemm_skinny")
         return
     check(lib.sb_gemm_splitk(C.byref(d), splits, partials.data_ptr(), slice_rows(a.B * a.T), _stream()), "sb_gemm_splitk")
+
+
+def gemm_decode(a: Seq, w: torch.Tensor, n: int, bias, act=ACT_NONE, out: Optional[Seq] = None,
+                prefetch: Optional[torch.Tensor] = None) -> Seq:
+    """out = act(a . w^T + bias) in fp16 for <= 256 rows on the transposed decoder-step kernel (sb_gemm_decode, direct mode)."""
+    lib = _lib.load()
+    assert a.PH == 0 and a.Tp == a.T
+    if out is None:
+        out = Seq(a.B, a.T, n)
+    d = GemmDesc()
+    d.a, d.a_rows, d.a_ld, d.c_in, d.taps, d.dil, d.a_row0 = a.buf.data_ptr(), a.B * a.T, a.buf.stride(0), a.C, 1, 1, 0
+    d.w, d.n, d.m = w.data_ptr(), n, a.B * a.T
+    d.bias, d.act = _p(bias), act
+    d.out, d.out_ld = out.buf.data_ptr(), out.buf.stride(0)
+    if prefetch is not None:
+        d.prefetch, d.prefetch_bytes = prefetch.data_ptr(), prefetch.numel() * prefetch.element_size()
+    check(lib.sb_gemm_decode(C.byref(d), 1, None, 0, _stream()), "sb_gemm_decode")
+    return out
 
 
 def splitk_reduce_ln(partials: torch.Tensor, splits: int, bias, x: Seq, ln_w, ln_b, h: Seq) -> None:

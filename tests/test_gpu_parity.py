@@ -121,6 +121,32 @@ def test_gemm_skinny_matches_simt_reference(ops, rows, n, k, splits):
     assert (part2.view(splits, SR, n)[:, :rows].sum(0) + bias - got).abs().max() < 1e-3
 
 
+@pytest.mark.parametrize("rows,n,k,splits", [(160, 3072, 1024, 6), (160, 1024, 8192, 16), (160, 8192, 1024, 1), (40, 384, 128, 2),
+                                             (5, 256, 128, 1), (256, 200, 192, 3), (33, 1126, 128, 1)])
+def test_gemm_decode_transposed_matches_simt_reference(ops, rows, n, k, splits):
+    """decode_gemm.cu (weights as the tcgen05 A operand, all rows as B): split-K partials sum to the product (uneven K
+    slices, ragged last feature tile, rows that are not a multiple of 16), and the direct mode applies bias + ReLU; both
+    against the CUDA-core reference kernel."""
+    from seamless_communication_b200.ops import Seq
+    torch.manual_seed(rows + n + splits)
+    a = Seq(1, rows, k, buf=torch.randn(rows, k, device=dev).half())
+    w = (torch.randn(n, k, device=dev) / math.sqrt(k)).half()
+    bias = torch.randn(n, device=dev)
+    want = ops.gemm_raw(a.buf, w, n, bias, act=ops.ACT_RELU, out_f32=True, ref=True)
+    SR = ops.slice_rows(rows)
+    part = torch.full((splits * SR, n), float("nan"), device=dev)
+    ops.gemm_splitk(a, w, n, splits, part, transposed=True)
+    got = part.view(splits, SR, n)[:, :rows].sum(0) + bias
+    assert torch.isnan(part.view(splits, SR, n)[:, rows:]).all()  # rows past `rows` are never written
+    assert (torch.relu(got) - want).abs().max() < 2e-3
+    out = Seq(1, rows, n)
+    out.buf.fill_(float("nan"))
+    ops.gemm_decode(a, w, n, bias, act=ops.ACT_RELU, out=out)
+    assert (out.buf.float() - want).abs().max() < 4e-3  # + fp16 rounding of the output
+    lin = ops.gemm_decode(a, w, n, None)
+    assert (lin.buf.float() - (a.buf.float() @ w.float().t())).abs().max() < 4e-3
+
+
 @pytest.mark.parametrize("taps,Cc", [(3, 16), (7, 16), (11, 32), (11, 8)])
 def test_gemm_narrow_channel_conv(ops, taps, Cc):
     """C < 64 with dilation 1 takes the overlapping-row (K-collapsed) tensor-map path."""
