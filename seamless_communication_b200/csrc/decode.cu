@@ -200,6 +200,137 @@ __global__ void __launch_bounds__(128) decode_self_attn_kernel(const elem_t* __r
   attend_one(qp, step + 1, kptr, vptr, sc, out + (long long)r * dim + hoff);
 }
 
+// Same computation with the dependent round trips removed (a kernel of this size costs ~1 us per DEPENDENT global access,
+// and the version above chains 13 of them: step, three slice gathers, ancestry, four key rounds, four value rounds):
+//   round 1: step index, every split-K slice of q | k | v, the whole ancestry row - all independent, requested together;
+//   then 32 keys per round with the key AND the value rows of the round in flight together (online softmax).
+__global__ void __launch_bounds__(128) decode_self_attn2_kernel(const float* __restrict__ part, int splits, long long slice_rows,
+                                                                const float* __restrict__ bias, elem_t* __restrict__ kcache,
+                                                                elem_t* __restrict__ vcache, const int* __restrict__ anc, int anc_ld,
+                                                                const int* __restrict__ step_ptr, int max_len,
+                                                                elem_t* __restrict__ out, int rows, int heads) {
+  extern __shared__ int sa_slots_all[];  // [4][max_len] ancestor slots
+  __shared__ __align__(16) elem_t s_new[4][3][HD];
+  pdl_sync();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, kg = lane >> 3, dc = lane & 7;
+  const int r = blockIdx.x;
+  const int h = blockIdx.y * 4 + warp;
+  if (h >= heads) return;
+  const int dim = heads * HD;
+  int* slots = sa_slots_all + warp * max_len;
+  // ---- round 1
+  const int step = *step_ptr;
+  const int* arow = anc + (long long)r * anc_ld;
+  int sl_reg[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) sl_reg[j] = (lane + 32 * j < max_len) ? arow[lane + 32 * j] : 0;
+  float2 acc[3];
+  const float* pp = part + (long long)r * 3 * dim + h * HD + 2 * lane;
+  const long long zs = slice_rows * 3LL * dim;
+#pragma unroll
+  for (int t = 0; t < 3; ++t) acc[t] = *reinterpret_cast<const float2*>(bias + t * dim + h * HD + 2 * lane);
+  for (int z0 = 0; z0 < splits; z0 += 4) {
+    float2 p[4][3];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int t = 0; t < 3; ++t)
+        p[u][t] = (z0 + u < splits) ? *reinterpret_cast<const float2*>(pp + (z0 + u) * zs + t * dim) : make_float2(0.f, 0.f);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int t = 0; t < 3; ++t) { acc[t].x += p[u][t].x; acc[t].y += p[u][t].y; }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if (lane + 32 * j < max_len) slots[lane + 32 * j] = sl_reg[j];
+  for (int t = lane + 128; t < step; t += 32) slots[t] = arow[t];  // max_len > 128
+#pragma unroll
+  for (int t = 0; t < 3; ++t) reinterpret_cast<__half2*>(s_new[warp][t])[lane] = __floats2half2_rn(acc[t].x, acc[t].y);
+  __syncwarp();
+  const elem_t *qp = s_new[warp][0], *knew = s_new[warp][1], *vnew = s_new[warp][2];
+  {  // persist the new K/V (slot r, position step)
+    elem_t* kd = kcache + ((long long)step * rows + r) * dim + h * HD;
+    elem_t* vd = vcache + ((long long)step * rows + r) * dim + h * HD;
+    reinterpret_cast<__half2*>(kd)[lane] = reinterpret_cast<const __half2*>(knew)[lane];
+    reinterpret_cast<__half2*>(vd)[lane] = reinterpret_cast<const __half2*>(vnew)[lane];
+  }
+  float q[8];
+  {
+    const uint4 u = *reinterpret_cast<const uint4*>(qp + dc * 8);
+    const __half2* hh = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(hh[e]); q[2 * e] = f.x; q[2 * e + 1] = f.y; }
+  }
+  const long long hoff = (long long)h * HD + dc * 8;
+  const int nkeys = step + 1;
+  float m = -INFINITY, l = 0.f, o[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) o[e] = 0.f;
+  for (int t0 = 0; t0 < nkeys; t0 += 32) {
+    uint4 ku[8], vu[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int t = t0 + 4 * i + kg;
+      if (t < step) {
+        const long long off = ((long long)t * rows + slots[t]) * dim + hoff;
+        ku[i] = *reinterpret_cast<const uint4*>(kcache + off);
+        vu[i] = *reinterpret_cast<const uint4*>(vcache + off);
+      } else if (t == step) {
+        ku[i] = *reinterpret_cast<const uint4*>(knew + dc * 8);
+        vu[i] = *reinterpret_cast<const uint4*>(vnew + dc * 8);
+      } else {
+        ku[i] = make_uint4(0, 0, 0, 0);
+        vu[i] = make_uint4(0, 0, 0, 0);
+      }
+    }
+    float sc[8], cm = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const __half2* hh = reinterpret_cast<const __half2*>(&ku[i]);
+      float a = 0.f;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(hh[e]); a += q[2 * e] * f.x + q[2 * e + 1] * f.y; }
+      a += __shfl_xor_sync(0xffffffffu, a, 1);
+      a += __shfl_xor_sync(0xffffffffu, a, 2);
+      a += __shfl_xor_sync(0xffffffffu, a, 4);
+      sc[i] = (t0 + 4 * i + kg < nkeys) ? a * 0.125f : -INFINITY;
+      cm = fmaxf(cm, sc[i]);
+    }
+    cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, 8));
+    cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, 16));
+    const float m_new = fmaxf(m, cm);  // finite: every round holds at least one valid key
+    const float scale = __expf(m - m_new);
+    m = m_new;
+    l *= scale;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] *= scale;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float pw = __expf(sc[i] - m);
+      l += pw;
+      const __half2* hh = reinterpret_cast<const __half2*>(&vu[i]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(hh[e]); o[2 * e] += pw * f.x; o[2 * e + 1] += pw * f.y; }
+    }
+  }
+  l += __shfl_xor_sync(0xffffffffu, l, 8);
+  l += __shfl_xor_sync(0xffffffffu, l, 16);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    o[e] += __shfl_xor_sync(0xffffffffu, o[e], 8);
+    o[e] += __shfl_xor_sync(0xffffffffu, o[e], 16);
+  }
+  if (kg == 0) {
+    const float inv = l > 0.f ? 1.f / l : 0.f;
+    uint4 w;
+    __half2* hh = reinterpret_cast<__half2*>(&w);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) hh[e] = __floats2half2_rn(o[2 * e] * inv, o[2 * e + 1] * inv);
+    *reinterpret_cast<uint4*>(out + (long long)r * dim + (long long)h * HD + dc * 8) = w;
+  }
+}
+
 __global__ void __launch_bounds__(128) decode_cross_attn_kernel(const elem_t* __restrict__ q, const float* __restrict__ part,
                                                                 int splits, long long slice_rows, const float* __restrict__ bias,
                                                                 const elem_t* __restrict__ k,
@@ -245,20 +376,39 @@ __global__ void __launch_bounds__(256) decode_cross_attn_shared_kernel(const flo
   const int b = blockIdx.x, h = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, kg = lane >> 3, dc = lane & 7;
   const int dim = heads * HD;
-  const int len = enc_lens ? min(enc_lens[b], s_enc) : s_enc;
   elem_t* ks = reinterpret_cast<elem_t*>(cs_smem);
   elem_t* vs = ks + (size_t)s_enc * HD;
   float* ps = reinterpret_cast<float*>(vs + (size_t)s_enc * HD) + warp * s_enc;
   elem_t* qs = reinterpret_cast<elem_t*>(reinterpret_cast<float*>(vs + (size_t)s_enc * HD) + (blockDim.x >> 5) * s_enc) + warp * HD;
   const elem_t* kb = k + (long long)b * s_enc * kv_ld + h * HD;
   const elem_t* vb = v + (long long)b * s_enc * kv_ld + h * HD;
-  for (int i = threadIdx.x; i < len * 8; i += blockDim.x) {
-    const int t = i >> 3, c = i & 7;
-    reinterpret_cast<uint4*>(ks)[i] = *reinterpret_cast<const uint4*>(kb + (long long)t * kv_ld + c * 8);
-    reinterpret_cast<uint4*>(vs)[i] = *reinterpret_cast<const uint4*>(vb + (long long)t * kv_ld + c * 8);
-  }
   const long long r = (long long)b * beam + warp;
+  // Every global read of the kernel is independent of the others: request them all before the first use (a kernel of this
+  // size costs one L2 round trip per DEPENDENT access; the valid length only masks the arithmetic, rows past it are read too).
+  const int n16 = s_enc * 8;
+  uint4 kreg[2], vreg[2];
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int i = threadIdx.x + j * blockDim.x;
+    if (i < n16) {
+      kreg[j] = *reinterpret_cast<const uint4*>(kb + (long long)(i >> 3) * kv_ld + (i & 7) * 8);
+      vreg[j] = *reinterpret_cast<const uint4*>(vb + (long long)(i >> 3) * kv_ld + (i & 7) * 8);
+    }
+  }
+  const int len = enc_lens ? min(enc_lens[b], s_enc) : s_enc;
   if (warp < beam) gather_head_vec(part, splits, slice_rows, dim, bias, r, h * HD, qs);
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int i = threadIdx.x + j * blockDim.x;
+    if (i < n16) {
+      reinterpret_cast<uint4*>(ks)[i] = kreg[j];
+      reinterpret_cast<uint4*>(vs)[i] = vreg[j];
+    }
+  }
+  for (int i = threadIdx.x + 2 * blockDim.x; i < n16; i += blockDim.x) {  // encoders longer than 64 (32) frames
+    reinterpret_cast<uint4*>(ks)[i] = *reinterpret_cast<const uint4*>(kb + (long long)(i >> 3) * kv_ld + (i & 7) * 8);
+    reinterpret_cast<uint4*>(vs)[i] = *reinterpret_cast<const uint4*>(vb + (long long)(i >> 3) * kv_ld + (i & 7) * 8);
+  }
   __syncthreads();
   if (warp >= beam) return;
   float q[8];
@@ -739,6 +889,15 @@ extern "C" int sb_decode_self_attn(const void* qkv, const float* qkv_partials, i
   SB_REQUIRE((qkv || (qkv_partials && qkv_bias && splits >= 1)) && kcache && vcache && anc && out && step_ptr && rows > 0 &&
                  heads > 0 && max_len > 0,
              SB_EINVAL, "sb_decode_self_attn: bad args");
+  static int v2 = -1;
+  if (v2 < 0) { const char* e = getenv("SB_SELF_ATTN_V2"); v2 = (e == nullptr || atoi(e) != 0) ? 1 : 0; }
+  if (v2 && qkv == nullptr && (size_t)4 * max_len * sizeof(int) <= 48 * 1024) {
+    SB_CUDA_OK(launch_k(decode_self_attn2_kernel, dim3(rows, (heads + 3) / 4), dim3(128), (size_t)4 * max_len * sizeof(int),
+                         (cudaStream_t)stream, qkv_partials, (int)splits, (long long)slice_rows, qkv_bias, (elem_t*)kcache, (elem_t*)vcache,
+                         (const int*)anc, (int)anc_ld, (const int*)step_ptr, (int)max_len, (elem_t*)out, (int)rows, (int)heads));
+    count_launch();
+    return SB_OK;
+  }
   size_t smem = (size_t)8 * max_len * sizeof(float);
   SB_REQUIRE(smem <= 48 * 1024, SB_ENOSUP, "sb_decode_self_attn: max_len %d too large", max_len);
   SB_CUDA_OK(launch_k(decode_self_attn_kernel, dim3(rows, (heads + 3) / 4), dim3(128), smem, (cudaStream_t)stream,
