@@ -17,7 +17,7 @@ typedef __half elem_t;  // storage / tensor-core input type of the whole path (t
 
 void set_error(const char* fmt, ...);
 extern long long g_launch_count;
-inline void count_launch(int n = 1) { g_launch_count += n; }
+inline void count_launch(int n = 1) { __atomic_fetch_add(&g_launch_count, (long long)n, __ATOMIC_RELAXED); }  // several host threads launch
 
 #define SB_REQUIRE(cond, code, ...)      \
   do {                                   \

@@ -926,7 +926,7 @@ extern "C" int sb_decoder_step(const sb_decoder_launch_t* l, sb_stream_t stream)
   attr[0].val.cooperative = 1;
   cfg.attrs = attr;
   cfg.numAttrs = l->cooperative ? 1 : 0;
-  static DsParams prm;  // 64-byte aligned copy of the opaque blob (CUtensorMap alignment); launches are issued from one host thread
+  static thread_local DsParams prm;  // 64-byte aligned copy of the opaque blob (CUtensorMap alignment), one per launching host thread
   memcpy(&prm, l->params, sizeof(prm));
   SB_CUDA_OK(cudaLaunchKernelEx(&cfg, pick_kernel(l->npad), prm));
   count_launch();

@@ -15,6 +15,7 @@ Weight packing (one-time, at load):
 from __future__ import annotations
 
 import collections
+import threading
 import ctypes as C
 import math
 import os
@@ -28,6 +29,7 @@ from .config import UnitYConfig, VocoderConfig
 from .ops import ACT_LRELU, ACT_NONE, ACT_RELU, ACT_SILU, F16, Seq
 
 I32 = torch.int32
+_CAPTURE_LOCK = threading.Lock()
 
 
 def sinusoid_table(max_len: int, dim: int, legacy_pad_idx: int = 1) -> torch.Tensor:
@@ -61,6 +63,12 @@ class UnitYEngine:
             self._build_char_tables()
         self._graphs = collections.OrderedDict()
         self._search_streams = []
+        # lanes (parallel.LanePool): several host threads drive independent batches on their own streams; each thread
+        # sees its own search states / graphs (the lane is part of the cache key) and its own "last search" record
+        self._tls = threading.local()
+        self._count_lock = threading.Lock()
+        self.search_priority = os.environ.get("SB_SEARCH_PRIORITY", "1") != "0"
+        self._state_lock = threading.RLock()
         self.search_groups = 1  # concurrent sentence groups in beam_search (see _search_group_count)
         self.decode_prefetch = os.environ.get("SB_DECODE_PREFETCH", "1") != "0"
         self.decode_skinny = os.environ.get("SB_DECODE_SKINNY", "1") != "0"  # <= 160 rows: skinny_gemm.cu
@@ -371,11 +379,31 @@ class UnitYEngine:
         check(lib.sb_beam_step(C.byref(st["beam_desc"]), stream), "sb_beam_step")
         check(lib.sb_step_advance(st["step"].data_ptr(), stream), "sb_step_advance")
 
+    @property
+    def lane(self) -> int:
+        return getattr(self._tls, "lane", 0)
+
+    def set_lane(self, lane: int):
+        """Bind the calling host thread to search-state lane `lane` (parallel.LanePool calls this once per worker)."""
+        self._tls.lane = int(lane)
+
+    @property
+    def _last_search_states(self):
+        return getattr(self._tls, "last_states", [])
+
+    @_last_search_states.setter
+    def _last_search_states(self, groups):
+        self._tls.last_states = groups
+
     def _search_state(self, B, S_enc, ML, beam, P, has_lens, use_graph, slot=0):
+        with self._state_lock:  # the cache is shared by the lanes' host threads
+            return self._search_state_locked(B, S_enc, ML, beam, P, has_lens, use_graph, slot)
+
+    def _search_state_locked(self, B, S_enc, ML, beam, P, has_lens, use_graph, slot):
         """Static buffers + captured CUDA graphs of one decoder step, cached per problem shape so that repeated
         predict() calls replay the same graphs (the reference rebuilds its generator per call, translator.py:179-186;
         construction here stays cheap after the first call)."""
-        key = (B, S_enc, ML, beam, P, has_lens, use_graph, slot, self.decode_fused)
+        key = (B, S_enc, ML, beam, P, has_lens, use_graph, slot, self.decode_fused, self.lane)
         st = self._graphs.get(key)
         if st is not None:
             self._graphs.move_to_end(key)
@@ -483,9 +511,9 @@ class UnitYEngine:
     def _evict_search_states(self, keep):
         """The cache is keyed by problem shape (S_enc and max_len follow the audio length), one entry holds the KV caches,
         the history and two CUDA graphs (~4.8 GB at 32 sentences x beam 5): least-recently-used entries are dropped once
-        the total exceeds SB_SEARCH_CACHE_GB (default 12), so a service fed variable-length audio cannot grow without
+        the total exceeds SB_SEARCH_CACHE_GB (default 40), so a service fed variable-length audio cannot grow without
         bound (the reference frees its search state after every call)."""
-        budget = float(os.environ.get("SB_SEARCH_CACHE_GB", "12")) * 2 ** 30
+        budget = float(os.environ.get("SB_SEARCH_CACHE_GB", "40")) * 2 ** 30
         sizes = {k: self._state_bytes(v) for k, v in self._graphs.items()}
         total = sum(sizes.values())
         for k in list(self._graphs.keys()):
@@ -549,6 +577,10 @@ class UnitYEngine:
 
     def _capture(self, st):
         """Capture the forward and the select halves of a decoder step (all pointers/shapes static)."""
+        with _CAPTURE_LOCK:  # one capture at a time in the process (launch counting + capture mode are process-wide)
+            self._capture_locked(st)
+
+    def _capture_locked(self, st):
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):  # eager warm-up: lazy one-time initialisation must not happen during capture
@@ -557,11 +589,11 @@ class UnitYEngine:
         torch.cuda.current_stream().wait_stream(s)
         n0 = ops.launch_count()
         st["g_fwd"] = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(st["g_fwd"]):
+        with torch.cuda.graph(st["g_fwd"], capture_error_mode="thread_local"):
             self._decoder_step_forward(st)
         n1 = ops.launch_count()
         st["g_sel"] = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(st["g_sel"]):
+        with torch.cuda.graph(st["g_sel"], capture_error_mode="thread_local"):
             self._decoder_step_select(st)
         st["n_fwd"], st["n_sel"] = n1 - n0, ops.launch_count() - n1
 
@@ -601,9 +633,11 @@ class UnitYEngine:
 
     def _search_step(self, st, use_graph, select=True):
         if use_graph:
-            st["g_fwd"].replay(); self.graph_kernels += st["n_fwd"]
+            st["g_fwd"].replay()
             if select:
-                st["g_sel"].replay(); self.graph_kernels += st["n_sel"]
+                st["g_sel"].replay()
+            with self._count_lock:
+                self.graph_kernels += st["n_fwd"] + (st["n_sel"] if select else 0)
         else:
             self._decoder_step_forward(st)
             if select:
@@ -641,9 +675,37 @@ class UnitYEngine:
         g = int(os.environ.get("SB_SEARCH_GROUPS", "0")) or self.search_groups
         return max(1, min(g, B // 4)) if B >= 8 else 1
 
+    def _priority_stream(self):
+        """The calling thread's high-priority stream for the search (SB_SEARCH_PRIORITY, default on).  A decoder step is a
+        chain of ~260 dependent kernels of a few microseconds; when other lanes (parallel.LanePool) have long GEMM grids
+        of the encoder / T2U / vocoder queued, a normal-priority step kernel waits until those grids have issued all their
+        CTAs.  On a high-priority stream its CTAs take the next free SM slots, so the searches keep moving underneath
+        the heavy stages of the other batches."""
+        if not self.search_priority:
+            return None
+        s = getattr(self._tls, "hp_stream", None)
+        if s is None:
+            s = self._tls.hp_stream = torch.cuda.Stream(device=self.device, priority=-1)
+        return s
+
     @torch.inference_mode()
     def beam_search(self, enc: Seq, enc_lens, prefix: List[int], beam=5, soft_max=(1, 200), hard_max=1024,
                     len_penalty=1.0, unk_penalty=0.0, min_seq_len=1, use_graph=True, cross_kv=None):
+        """Device-resident beam search (see _beam_search); runs on the thread's high-priority stream, ordered after the
+        caller's stream on entry and before it on exit."""
+        hp = self._priority_stream()
+        args = (enc, enc_lens, prefix, beam, soft_max, hard_max, len_penalty, unk_penalty, min_seq_len, use_graph, cross_kv)
+        if hp is None:
+            return self._beam_search(*args)
+        cur = torch.cuda.current_stream()
+        hp.wait_stream(cur)
+        with torch.cuda.stream(hp):
+            out = self._beam_search(*args)
+        cur.wait_stream(hp)
+        return out
+
+    def _beam_search(self, enc: Seq, enc_lens, prefix: List[int], beam=5, soft_max=(1, 200), hard_max=1024,
+                     len_penalty=1.0, unk_penalty=0.0, min_seq_len=1, use_graph=True, cross_kv=None):
         """Device-resident beam search.  Returns per sentence the finished hypotheses [(score, ids)], best first
         (semantics: fairseq2.cpp:1371-1608; see decode.cu).  `cross_kv` is ignored (kept for API stability): the
         static cross-attention K/V of the cached search state are recomputed from `enc`."""

@@ -622,6 +622,39 @@ def test_translator_predict_s2st_and_s2tt(tiny):
         tr.predict("hello", "t2tt", "spa")  # src_lang missing (translator.py:295-296)
 
 
+def test_lanes_concurrent_batches_equal_serial(tiny):
+    """parallel.LanePool: batches in flight on separate streams / host threads, each with its own search state, return
+    exactly what the same batches return one at a time (the kernels are deterministic; the lanes share only the weights)."""
+    from seamless_communication_b200.inference import SequenceGeneratorOptions, Translator
+    from seamless_communication_b200.parallel import LanePool
+    tr = Translator(tiny["model"], tiny["voc"], device="cuda")
+    eng = tiny["model"].engine
+    opts = SequenceGeneratorOptions(beam_size=5, soft_max_seq_len=(1, 200), hard_max_seq_len=24)
+    batches = [S.make_waveforms(3, 32000, seed=100 + i).cuda() for i in range(7)]
+
+    def step(w):
+        texts, speech = tr.predict(tr.fbank_batch(w), "s2st", "spa", text_generation_opts=opts)
+        return texts, speech.units, [a.float().cpu() for a in speech.audio_wavs]
+
+    serial = [step(w) for w in batches]
+    torch.cuda.synchronize()
+    pool = LanePool("cuda", 3, [eng])
+    try:
+        pool.warm(step, batches[0])
+        for _ in range(2):  # second round: every lane's graphs exist, all three lanes run concurrently from the start
+            got = pool.map(step, [(w,) for w in batches])
+            for (t0, u0, a0), (t1, u1, a1) in zip(serial, got):
+                assert t0 == t1 and u0 == u1
+                for x, y in zip(a0, a1):
+                    assert torch.equal(x, y)
+        assert len({k[-1] for k in eng._graphs if k[0] == 3}) >= 3  # one search state per lane
+        # a failing job surfaces through its future
+        with pytest.raises(ZeroDivisionError):
+            pool.submit(0, lambda: 1 // 0).result()
+    finally:
+        pool.close()
+
+
 # ------------------------------------------------------------------------------------------------ properties at full width
 def test_full_width_properties_permutation_padding_determinism(small, ops):
     """M=1024 / 16 heads / 10 s audio (the BASELINE tile shapes), too big for the CPU oracle in a unit test:

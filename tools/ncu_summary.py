@@ -20,10 +20,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def short(name):
-    name = re.sub(r"\(anonymous namespace\)::", "", name)
+    name = re.sub(r"\(anonymous namespace\)::|<unnamed>::", "", name)
     name = re.sub(r"^void ", "", name)
-    m = re.match(r"(sb::)?([A-Za-z0-9_]+)(<[^>]*>)?", name)
-    return (m.group(2) + (m.group(3) or "")) if m else name[:60]
+    name = re.sub(r"^(sb::|at::native::|at::)+", "", name)
+    m = re.match(r"([A-Za-z0-9_]+)(<[^>]*>)?", name)
+    return (m.group(1) + (m.group(2) or "")) if m else name[:60]
 
 
 def main():
