@@ -403,7 +403,7 @@ def run_stream(args, device):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=12)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--config", default="s2st", choices=sorted(CONFIGS) + ["stream"])
@@ -586,7 +586,7 @@ def main():
             "serial": {"ms_per_step": ms_serial, "value": world * BATCH / (ms_serial * 1e-3), "unit": "utt/s",
                        "what": "the same step with one batch in flight (latency of a batch; SB_LANES=1 makes this the headline)"},
             "e2e": {"value": e2e_value, "unit": "utt/s", "h2d_bytes_per_step": xch.h2d_bytes, "d2h_bytes_per_step": xch.d2h_bytes,
-                    "ms_per_step": ms_e2e, "overlap": "inputs of step i+1 and outputs of step i-1 move on side streams"},
+                    "ms_per_step": ms_e2e, "overlap": "inputs of later steps and outputs of earlier steps move on side streams (exchange on the main thread, compute on the lanes)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
