@@ -67,7 +67,7 @@ class UnitYEngine:
         # sees its own search states / graphs (the lane is part of the cache key) and its own "last search" record
         self._tls = threading.local()
         self._count_lock = threading.Lock()
-        self.search_priority = os.environ.get("SB_SEARCH_PRIORITY", "1") != "0"
+        self.search_priority = os.environ.get("SB_SEARCH_PRIORITY", "0") != "0"
         self._state_lock = threading.RLock()
         self.search_groups = 1  # concurrent sentence groups in beam_search (see _search_group_count)
         self.decode_prefetch = os.environ.get("SB_DECODE_PREFETCH", "1") != "0"
@@ -676,11 +676,11 @@ class UnitYEngine:
         return max(1, min(g, B // 4)) if B >= 8 else 1
 
     def _priority_stream(self):
-        """The calling thread's high-priority stream for the search (SB_SEARCH_PRIORITY, default on).  A decoder step is a
-        chain of ~260 dependent kernels of a few microseconds; when other lanes (parallel.LanePool) have long GEMM grids
-        of the encoder / T2U / vocoder queued, a normal-priority step kernel waits until those grids have issued all their
-        CTAs.  On a high-priority stream its CTAs take the next free SM slots, so the searches keep moving underneath
-        the heavy stages of the other batches."""
+        """The calling thread's high-priority stream for the search (SB_SEARCH_PRIORITY=1; default off).  The idea: a
+        decoder step is a chain of ~260 dependent kernels of a few microseconds, and when other lanes (parallel.LanePool)
+        have long GEMM grids of the encoder / T2U / vocoder queued, a high-priority step kernel could take the next free
+        SM slots instead of waiting behind them.  Measured on B200 (profiles/r02_lane_sweep.txt): no difference at 2-4
+        lanes (139 / 152 / 156 utt/s either way), so the search stays on the caller's stream."""
         if not self.search_priority:
             return None
         s = getattr(self._tls, "hp_stream", None)
