@@ -296,12 +296,16 @@ def decode_step_bytes(eng, batch, steps_dec):
 
 
 def measured_decode_traffic():
-    """DRAM bytes of one beam-search step from this round's ncu pass (tools/ncu_summary.py -> profiles/r02_decode_step_dram.json)."""
-    p = os.path.join(ROOT, "profiles", "r02_decode_step_dram.json")
-    if not os.path.exists(p):
-        return None, None
-    d = json.load(open(p))
-    return d.get("dram_bytes_per_step"), d.get("source")
+    """DRAM bytes of one beam-search step from this round's ncu passes over `bench.py --profile-only` with a 13-step search
+    (tools/ncu_summary.py).  Two passes: `--cache-control none` (L2 contents carried from kernel to kernel, as in a real
+    step: split-K partials and activations stay in L2) is the figure reported as `traffic`; the default pass flushes the
+    caches before every launch, so every intermediate is counted as DRAM traffic (`traffic_cold`)."""
+    out = {}
+    for key, name in (("warm", "r02warm_decode_step_dram.json"), ("cold", "r02_decode_step_dram.json")):
+        p = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(p):
+            out[key] = json.load(open(p))
+    return out
 
 
 def stage_table(stages, batch, pk, eng, task):
@@ -598,11 +602,21 @@ def main():
             line["stages_ms"] = stages
             line["stages"] = tab
             bs = tab["beam_search"]
-            traffic, tsrc = measured_decode_traffic() if task == "s2st" else (None, None)
+            tm = measured_decode_traffic() if task == "s2st" else {}
+            tsel = tm.get("warm") or tm.get("cold")
+            traffic = tsel["dram_bytes_per_step"] if tsel else None
+            tsrc = None
+            if tsel:
+                alg_prof, _ = decode_step_bytes(eng, BATCH, tsel["steps_profiled"])
+                tsrc = (f"ncu dram__bytes_read.sum + dram__bytes_write.sum over the launches of a {tsel['steps_profiled']}-step search, per step "
+                        f"({'--cache-control none' if 'warm' in tm else 'caches flushed per launch'}; profiles/r02warm_kernels_ncu.txt, "
+                        f"profiles/r02_kernels_ncu.txt); algorithmic bytes at those positions: {alg_prof / 1e9:.2f} GB + 0.16 GB of fp32 "
+                        f"logits the step also writes; the search's K/V reads grow with the position")
             line["roofline"] = {"bound": "hbm", "kernel": "one beam-search step = decoder-step kernels + vocabulary projection + top-K "
                                                           f"({bs['steps']} steps, {100 * bs['ms'] / ms_serial:.0f} % of a batch's time)",
                                 "achieved": bs["achieved_gbs"], "peak": pk["hbm"], "unit": "GB/s", "frac": bs["frac"],
-                                "traffic": traffic, "traffic_source": tsrc, "algorithmic_bytes": bs["algorithmic_bytes_per_step"],
+                                "traffic": traffic, "traffic_cold": (tm.get("cold") or {}).get("dram_bytes_per_step"),
+                                "traffic_source": tsrc, "algorithmic_bytes": bs["algorithmic_bytes_per_step"],
                                 "ms_per_launch_group": bs["ms_per_step"], "peak_source": pk["src"], "in_flight": 1}
             if pool is not None:
                 # how the step actually runs: LANES searches interleaved on the device.  Every lane's step still needs every
