@@ -165,9 +165,10 @@ class LanePool:
 
     def __init__(self, device, lanes: int, engines: Sequence = ()):
         self.device, self.lanes, self.engines = torch.device(device), int(lanes), list(engines)
-        if self.device.index is None:  # "cuda" -> the caller's current device (the workers need an explicit index)
+        self.cuda = self.device.type == "cuda"  # on "cpu" (host-logic tests) the lanes are plain threads: no streams / events
+        if self.cuda and self.device.index is None:  # "cuda" -> the caller's current device (the workers need an explicit index)
             self.device = torch.device("cuda", torch.cuda.current_device())
-        self.streams = [torch.cuda.Stream(self.device) for _ in range(self.lanes)]
+        self.streams = [torch.cuda.Stream(self.device) if self.cuda else None for _ in range(self.lanes)]
         self.queues = [queue.SimpleQueue() for _ in range(self.lanes)]
         self.threads = [threading.Thread(target=self._run, args=(i,), daemon=True, name=f"lane{i}") for i in range(self.lanes)]
         for t in self.threads:
@@ -176,7 +177,8 @@ class LanePool:
     def _run(self, i: int):
         setup_error = None
         try:
-            torch.cuda.set_device(self.device)
+            if self.cuda:
+                torch.cuda.set_device(self.device)
             for e in self.engines:
                 e.set_lane(i)
         except BaseException as e:  # every job of this lane then fails with it instead of waiting forever
@@ -191,6 +193,10 @@ class LanePool:
                 fut.set_exception(setup_error)
                 continue
             try:
+                if not self.cuda:
+                    with torch.inference_mode():
+                        fut.set_result((fn(*args), None))
+                    continue
                 with torch.inference_mode(), torch.cuda.stream(s):
                     if after is not None:
                         s.wait_event(after)
@@ -210,7 +216,8 @@ class LanePool:
         """Run fn once on every lane, one lane at a time (first use captures the lane's CUDA graphs)."""
         for i in range(self.lanes):
             self.submit(i, fn, *args).result()
-        torch.cuda.synchronize(self.device)
+        if self.cuda:
+            torch.cuda.synchronize(self.device)
 
     def map(self, fn: Callable, arg_lists: Sequence[Sequence]) -> list:
         """fn(*args) for every args in arg_lists, round-robin over the lanes; results in order, device work complete."""
@@ -218,7 +225,8 @@ class LanePool:
         outs = []
         for f in futs:
             out, ev = f.result()
-            ev.synchronize()
+            if ev is not None:
+                ev.synchronize()
             outs.append(out)
         return outs
 

@@ -342,3 +342,50 @@ def test_model_loaders_refuse_to_invent_weights():
         load_unity_model("seamlessM4T_v2_large", device="cpu")
     with pytest.raises(RuntimeError, match="synthetic=True"):
         load_vocoder_model("vocoder_v2", device="cpu")
+
+
+def test_lane_pool_host_logic():
+    """parallel.LanePool without a GPU: every lane is one thread bound to one engine lane, jobs of a lane run in
+    submission order, results come back in order, a failing job (or a failing lane set-up) surfaces through its future."""
+    import threading
+    import time
+    from seamless_communication_b200.parallel import LanePool
+
+    class FakeEngine:
+        def __init__(self):
+            self.tls = threading.local()
+
+        def set_lane(self, i):
+            self.tls.lane = i
+
+    eng = FakeEngine()
+    pool = LanePool("cpu", 3, [eng])
+    log = []
+
+    def job(i):
+        time.sleep(0.01 * (5 - i % 5))  # later jobs finish earlier unless the lane serialises them
+        log.append((eng.tls.lane, i))
+        return eng.tls.lane, i
+
+    try:
+        outs = pool.map(job, [(i,) for i in range(9)])
+        assert outs == [(i % 3, i) for i in range(9)]  # round-robin lanes, results in submission order
+        for lane in range(3):
+            assert [i for l, i in log if l == lane] == [lane, lane + 3, lane + 6]  # in-lane order kept
+        pool.warm(job, 0)
+        with pytest.raises(ZeroDivisionError):
+            pool.submit(1, lambda: 1 // 0).result(timeout=10)
+        assert pool.submit(1, lambda: 7).result(timeout=10)[0] == 7  # the lane survives a failed job
+    finally:
+        pool.close()
+
+    class BrokenEngine:
+        def set_lane(self, i):
+            raise RuntimeError("no such lane")
+
+    pool = LanePool("cpu", 1, [BrokenEngine()])
+    try:
+        with pytest.raises(RuntimeError, match="no such lane"):
+            pool.submit(0, lambda: 1).result(timeout=10)
+    finally:
+        pool.close()

@@ -1,8 +1,16 @@
 import ctypes as C, os, sys, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from seamless_communication_b200 import _lib
-lib = C.CDLL(_lib.LIB_PATH)
+import subprocess
+# the probe is a tool, not part of the product library: built on first use into tools/_build/ (nvcc cross-compiles sm_100a)
+SRC, OUT = os.path.join(ROOT, "tools", "tma_probe.cu"), os.path.join(ROOT, "tools", "_build", "libtma_probe.so")
+CSRC = os.path.join(ROOT, "seamless_communication_b200", "csrc")
+if not os.path.exists(OUT) or os.path.getmtime(OUT) < os.path.getmtime(SRC):
+    os.makedirs(os.path.dirname(OUT), exist_ok=True)
+    subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-shared",
+                           "-Xcompiler", "-fPIC", "-I", CSRC, "-I", os.path.join(ROOT, "include"), SRC,
+                           os.path.join(CSRC, "library.cu"), "-o", OUT, "-lcuda"])
+lib = C.CDLL(OUT)
 lib.sb_tma_probe.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
 rows, ld = 1 << 18, 1024  # 512 MB fp16
 buf = torch.randn(rows, ld, device="cuda").half()
