@@ -60,7 +60,9 @@ template <int BN, bool DEEP = false>
 struct TileCfg {
   // DEEP: one CTA per SM with as many stages as fit - for skinny problems (few CTAs) whose K loop is a chain of
   // ~1.4 us load round trips (tools/gemm_timeline.py); the default keeps 2 CTAs/SM so epilogues overlap main loops
-  static constexpr int STAGES = DEEP ? (BN >= 128 ? 6 : 8) : ((BN >= 128) ? 3 : 4);
+  // BN = 256: two stages of 48 KB keep 2 CTAs/SM (TMEM 2 x 256 columns) while every A tile feeds twice the columns:
+  // 85 instead of 64 FLOP per byte moved L2 -> SM, the bound of the 128-wide tiles (profiles/r01_notes.md)
+  static constexpr int STAGES = DEEP ? (BN >= 128 ? 6 : 8) : (BN >= 256 ? 2 : (BN >= 128) ? 3 : 4);
   static constexpr int B_TILE_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
   // Accumulating tcgen05.mma instructions that target the same TMEM tile issue ~180 cycles apart (measured:
@@ -74,9 +76,12 @@ struct TileCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + BN * 4;
   static constexpr int THREADS = 32 * (5 + STAGES);
   // epilogue staging reuses the (drained) pipeline stages: out groups first, out2 groups after them
-  static constexpr int OUT_GROUPS_MAX = BN * 4 / 128;  // fp32 worst case: 32 columns per 16 KB group
+  // fp32 worst case: 32 columns per 16 KB group; the 256-wide tile stages fp16 outputs only (no fp32 / second output: the
+  // host never selects it for those)
+  static constexpr int OUT_GROUPS_MAX = BN >= 256 ? BN * 2 / 128 : BN * 4 / 128;
   static constexpr int OUT2_OFFSET = OUT_GROUPS_MAX * 16384;
-  static_assert(OUT2_OFFSET + (BN / 64 > 0 ? BN / 64 : 1) * 16384 <= STAGES * STAGE_BYTES, "staging does not fit");
+  static_assert(BN >= 256 || OUT2_OFFSET + (BN / 64 > 0 ? BN / 64 : 1) * 16384 <= STAGES * STAGE_BYTES, "staging does not fit");
+  static_assert(OUT_GROUPS_MAX * 16384 <= STAGES * STAGE_BYTES, "staging does not fit");
 };
 
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, const void* smem_src, int c0, int c1) {
@@ -628,6 +633,10 @@ extern "C" int sb_gemm(const sb_gemm_t* g_in, sb_stream_t stream) {
     SB_REQUIRE(!g->glu && g->n >= 128, SB_ENOSUP, "sb_gemm: tile_stats needs n >= 128 and no GLU");
     return sb::launch<128>(g, st);  // the statistics are per 128-column tile (SB_STATS_TILE)
   }
+  // 256-wide tiles for the large products (encoder / T2U / vocoder GEMMs): fp16 single-output epilogues, whole tiles only
+  static int bn256 = -1;
+  if (bn256 < 0) { const char* e = getenv("SB_GEMM_BN256"); bn256 = (e == nullptr || atoi(e) != 0) ? 1 : 0; }
+  if (bn256 && (g->n % 256) == 0 && !g->out_f32 && g->out2 == nullptr && tiles(256) >= 2 * 148) return sb::launch<256>(g, st);
   // largest N tile that still gives every SM two CTAs; fall back to smaller tiles for skinny problems
   if (g->n >= 128 && tiles(128) >= 148) return sb::launch<128>(g, st);
   if (g->n >= 64 && tiles(64) >= 148) return sb::launch<64>(g, st);

@@ -64,6 +64,43 @@ def test_gemm_linear(ops, m, n, k):
         assert rel(out, ref) < 2e-3 and rel(out, simt) < 2e-3  # fp16 inputs, fp32 accumulate; fp16 output rounding
 
 
+def test_gemm_wide_tiles_256(ops):
+    """gemm_tc_kernel<256> (two 48 KB stages, 2 CTAs/SM) is selected for fp16 single-output products with n % 256 == 0
+    and >= 296 tiles - the encoder / T2U / vocoder shapes: every epilogue it serves against fp32 torch (bias, SiLU, GLU,
+    residual + scales, conv taps over a ragged sequence batch with zeroed padding)."""
+    from seamless_communication_b200.ops import Seq
+    torch.manual_seed(256)
+    m, k = 10000, 320  # 79 M tiles x (n / 256) >= 296 for n >= 1024
+    a = (torch.randn(m, k, device=dev) * 0.5).half()
+    for n in (1024, 1280):
+        w = (torch.randn(n, k, device=dev) * 0.05).half()
+        bias = torch.randn(n, device=dev)
+        ref = a.float() @ w.float().t() + bias
+        out = ops.gemm_raw(a, w, n, bias)
+        assert rel(out, ref) < 2e-3 and rel(out, ops.gemm_raw(a, w, n, bias, ref=True)) < 2e-3
+        assert rel(ops.gemm_raw(a, w, n, bias, act=ops.ACT_SILU), F.silu(ref)) < 2e-3
+        assert rel(ops.gemm_raw(a, w, n, bias, glu=True), ref[:, 0::2] * torch.sigmoid(ref[:, 1::2])) < 2e-3
+        r1 = torch.randn(m, n, device=dev).half()
+        assert rel(ops.gemm_raw(a, w, n, bias, alpha=0.5, res1=r1), ref * 0.5 + r1.float()) < 2e-3
+    # 3-tap conv over sequences (full, ragged, empty): halo / padded rows exactly zero
+    B, T, Cc, N, taps = 40, 300, 128, 1024, 3
+    lens = torch.full((B,), T, dtype=torch.int32, device=dev)
+    lens[1], lens[2] = 77, 0
+    x = Seq(B, T, Cc, halo=1, lens=lens)
+    x.data().copy_((torch.randn(B, T, Cc, device=dev) * 0.5).half())
+    w = (torch.randn(N, taps * Cc, device=dev) * 0.05).half()
+    bias = torch.randn(N, device=dev)
+    res = x.like(C=N, zero=True)
+    res.data().copy_(torch.randn(B, T, N, device=dev).half())
+    o = ops.gemm(x, w, N, bias, taps=taps, act=ops.ACT_RELU, res1=res, alpha=0.5)
+    y = F.conv1d(x.data().float().transpose(1, 2), w.float().view(N, taps, Cc).permute(0, 2, 1), bias, padding=1).transpose(1, 2)
+    y = (F.relu(y) * 0.5 + res.data().float()) * (torch.arange(T, device=dev)[None] < lens[:, None])[:, :, None]
+    assert rel(o.data(), y) < 2e-3
+    full = o.buf.float().view(B, o.Tp, N)
+    assert full[:, :o.PH].abs().max() == 0 and full[:, o.PH + T:].abs().max() == 0
+    assert full[1, o.PH + 77:].abs().max() == 0 and full[2].abs().max() == 0
+
+
 @pytest.mark.parametrize("taps,dil", [(1, 1), (3, 1), (7, 1), (11, 5), (3, 3)])
 def test_gemm_conv_mask_residual_dual_output(ops, taps, dil):
     from seamless_communication_b200.ops import Seq
