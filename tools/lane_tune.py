@@ -16,11 +16,9 @@ CONFIGS = [
     ("skinny attn+qkv", dict(skinny_sites={"attn", "qkv"})),
     ("skinny attn+ffn2", dict(skinny_sites={"attn", "ffn2"})),
     ("skinny all", dict(skinny_sites={"attn", "qkv", "ffn1", "ffn2"})),
-    ("skinny none", dict(skinny_sites=set())),
     ("attn splits 4", dict(skinny_splits=(4, 4, 16))),
     ("attn splits 16", dict(skinny_splits=(4, 16, 16))),
     ("no prefetch", dict(decode_prefetch=False)),
-    ("gemm_t, no prefetch", dict(decode_gemm_t=True, decode_prefetch=False)),
 ]
 
 
