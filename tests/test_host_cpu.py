@@ -389,3 +389,93 @@ def test_lane_pool_host_logic():
             pool.submit(0, lambda: 1).result(timeout=10)
     finally:
         pool.close()
+
+
+def test_evaluate_driver_files_order_and_corrupted_inputs(tmp_path):
+    """seamless_communication_b200.evaluate.run_eval (the reference's cli/m4t/evaluate driver, evaluate.py:116-366) with a
+    stub translator: manifest parsing (TSV + JSON lines), WAV decoding (PCM16 / float32 / stereo), buckets in file order,
+    undecodable and NaN inputs replaced by the reference's dummy outputs, a RuntimeError batch skipped, output files."""
+    import json
+    import wave as wave_mod
+    from pathlib import Path
+    from seamless_communication_b200 import evaluate as E
+    from seamless_communication_b200.inference.translator import BatchedSpeechOutput
+
+    audio = tmp_path / "audio"
+    audio.mkdir()
+    g = torch.Generator().manual_seed(0)
+    lengths = [16000, 12000, 8000, 20000, 4000, 6000, 10000]
+    for i, n in enumerate(lengths):
+        x = torch.rand(n, generator=g) * 0.5 - 0.25
+        if i == 1:  # stereo PCM16 through the standard library writer: channel 0 is used
+            with wave_mod.open(str(audio / f"{i}.wav"), "wb") as w:
+                w.setnchannels(2); w.setsampwidth(2); w.setframerate(16000)
+                st = torch.stack([x, -x], dim=1)
+                w.writeframes((st * 32767).round().to(torch.int16).numpy().tobytes())
+        elif i == 2:
+            x[100] = float("nan")
+            E.write_wav_f32(audio / f"{i}.wav", x)
+        elif i == 4:
+            (audio / f"{i}.wav").write_bytes(b"not a wav file")
+        else:
+            E.write_wav_f32(audio / f"{i}.wav", x)
+    got = E.decode_wav(audio / "1.wav")
+    assert got.shape == (12000,) and got.abs().max() <= 0.25 + 1e-3
+    assert E.decode_wav(audio / "4.wav") is None and E.decode_wav(audio / "missing.wav") is None
+    back = E.decode_wav(audio / "0.wav")
+    assert back.shape == (16000,) and back.dtype == torch.float32
+
+    tsv = tmp_path / "dev.tsv"
+    tsv.write_text("id\taudio\ttgt_text\n" + "".join(f"{i}\t{i}.wav\tref {i}\n" for i in range(len(lengths))))
+
+    class StubTranslator:
+        device = torch.device("cpu")
+        calls = []
+
+        def fbank_batch(self, batch, lens):
+            return {"seqs": batch, "seq_lens": lens, "is_ragged": True}
+
+        def predict(self, src, task, tgt_lang, **kw):
+            lens = src["seq_lens"].tolist()
+            self.calls.append(lens)
+            if 20000 in lens:
+                raise RuntimeError("The sequence generator returned no hypothesis at index 0. Please file a bug report.")
+            assert src["seqs"].shape == (len(lens), max(lens)) and task == "s2st" and tgt_lang == "spa"
+            return ([f"hyp {n}" for n in lens],
+                    BatchedSpeechOutput(units=[[n % 7, 3] for n in lens], audio_wavs=[torch.full((1, 1, n // 10), 0.5) for n in lens]))
+
+    ctx = E.EvalContext(task="s2st", data_file=tsv, audio_root_dir=audio, target_lang="spa", output_path=tmp_path / "out", batch_size=2)
+    tr = StubTranslator()
+    res = E.run_eval(tr, ctx, lanes=2)
+    # buckets: (0,1) ok | (2 NaN,3 -> RuntimeError batch skipped) | (4 undecodable, 5) | (6)
+    assert sorted(map(tuple, tr.calls)) == sorted([(16000, 12000), (20000,), (6000,), (10000,)])
+    assert res["samples"] == 5 and res["skipped"] == 2 and res["corrupted"] == 2
+    lines = res["model_outputs"].read_text().splitlines()
+    assert lines[0] == "ref_tgt_text\tpred_tgt_text\tpred_tgt_audio"
+    body = [l.split("\t") for l in lines[1:]]
+    assert [b[:2] for b in body] == [["ref 0", "hyp 16000"], ["ref 1", "hyp 12000"], ["ref 4", ""], ["ref 5", "hyp 6000"],
+                                      ["ref 6", "hyp 10000"]]
+    units = res["unit_outputs"].read_text().splitlines()
+    assert units == ["5 3", "2 3", "", "1 3", "4 3"]
+    wavs = [E.decode_wav(Path(b[2])) for b in body]
+    assert [w.numel() for w in wavs] == [1600, 1200, 16000, 600, 1000]  # the dummy is one second of silence
+    assert wavs[2].abs().max() == 0 and abs(float(wavs[0][0]) - 0.5) < 1e-6
+    assert [Path(b[2]).name for b in body] == [f"{i}_pred.wav" for i in range(5)]
+
+    # JSON-lines manifest (m4t_prepare_dataset layout), text output only
+    js = tmp_path / "dev.json"
+    js.write_text("".join(json.dumps({"source": {"text": "s", "lang": "eng", "audio_local_path": f"{i}.wav"},
+                                      "target": {"text": f"ref {i}"}}) + "\n" for i in (0, 5)))
+
+    class TextStub(StubTranslator):
+        def predict(self, src, task, tgt_lang, **kw):
+            return [f"hyp {n}" for n in src["seq_lens"].tolist()], None
+
+    from seamless_communication_b200.inference.translator import Modality
+    ctx2 = E.EvalContext(task="s2tt", data_file=js, audio_root_dir=audio, target_lang="spa", output_path=tmp_path / "out",
+                         output_modality=Modality.TEXT, batch_size=4)
+    res2 = E.run_eval(TextStub(), ctx2)
+    assert res2["model_outputs"].read_text().splitlines() == ["ref_tgt_text\tpred_tgt_text", "ref 0\thyp 16000", "ref 5\thyp 6000"]
+    with pytest.raises(NotImplementedError):
+        E.run_eval(TextStub(), E.EvalContext(task="t2tt", data_file=js, audio_root_dir=audio, target_lang="spa",
+                                             output_path=tmp_path / "out", input_modality=Modality.TEXT))
