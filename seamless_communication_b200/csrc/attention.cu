@@ -511,8 +511,11 @@ extern "C" int sb_attention(const void* q, int64_t q_ld, const void* k, int64_t 
   a.batch = batch; a.heads = heads; a.sq = sq; a.sk = sk; a.q_rows = q_rows; a.q_halo = q_halo;
   a.kv_rows = kv_rows; a.kv_halo = kv_halo; a.kv_lens = kv_lens; a.causal = causal;
   a.rel_k = (const elem_t*)rel_k; a.rel_left = rel_left; a.rel_right = rel_right;
+  // opt-in: measured on B200 at the encoder shape (tools/attn_bench.py) the 128-row kernel is SLOWER, 457 vs 316 us per
+  // launch: 242 registers and 108 KB leave 8 warps per SM against 12, and with one warp doing QK^T -> softmax -> PV in turn
+  // the tensor pipe idles during the softmax unless other warps fill in; shared-memory bandwidth was not the limit
   static int v2 = -1;
-  if (v2 < 0) { const char* e = getenv("SB_ATTENTION_V2"); v2 = (e == nullptr || atoi(e) != 0) ? 1 : 0; }
+  if (v2 < 0) { const char* e = getenv("SB_ATTENTION_V2"); v2 = (e != nullptr && atoi(e) != 0) ? 1 : 0; }
   if (v2) {
     size_t smem = (size_t)(AQ2 + 4 * AK) * LDS * sizeof(elem_t);
     if (rel_k) smem += (size_t)REL_MAX * LDS * sizeof(elem_t) + 4 * 32 * (REL_MAX + 1) * sizeof(float);

@@ -634,8 +634,8 @@ extern "C" int sb_gemm(const sb_gemm_t* g_in, sb_stream_t stream) {
     return sb::launch<128>(g, st);  // the statistics are per 128-column tile (SB_STATS_TILE)
   }
   // 256-wide tiles for the large products (encoder / T2U / vocoder GEMMs): fp16 single-output epilogues, whole tiles only
-  static int bn256 = -1;
-  if (bn256 < 0) { const char* e = getenv("SB_GEMM_BN256"); bn256 = (e == nullptr || atoi(e) != 0) ? 1 : 0; }
+  const char* e256 = getenv("SB_GEMM_BN256");  // read per call: tools toggle it inside one process
+  const int bn256 = (e256 == nullptr || atoi(e256) != 0) ? 1 : 0;
   if (bn256 && (g->n % 256) == 0 && !g->out_f32 && g->out2 == nullptr && tiles(256) >= 2 * 148) return sb::launch<256>(g, st);
   // largest N tile that still gives every SM two CTAs; fall back to smaller tiles for skinny problems
   if (g->n >= 128 && tiles(128) >= 148) return sb::launch<128>(g, st);
