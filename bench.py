@@ -212,6 +212,13 @@ def cpu_baseline_block(task, batch, timed_runs, warmup=True, trace=None):
     return block, out
 
 
+def workload_config(cfg, batch, world):
+    """`config` of the bench line: the workload only, identical in both arms (how this arm runs it is under `pipeline`)."""
+    return {"workload": cfg["workload"], "per_gpu_batch": batch, "global_batch": batch * world, "parallelism": f"dp{world}",
+            "l2": "working set (3.5 GB fp16 weights + activations) >> 126 MB L2, no explicit flush",
+            "weights": "random-init, seeded", "accumulate": "f32"}
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -222,7 +229,9 @@ def run_reference(args, rank):
             "steps": len(block["seconds_per_run"]), "warmup": 1 if args.warmup > 0 else 0,
             "ms_per_step": 1e3 * statistics.mean(block["seconds_per_run"]), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": cfg["workload"], "sample": "each step = batch 4 of the workload's utterances on the host CPU"},
+            "config": workload_config(cfg, cfg["batch"], max(1, args.gpus)),
+            "sample": "each step = batch 4 of the workload's utterances on the host CPU (BASELINE.md 3 protocol: 1 warm-up, "
+                      "at most 3 timed runs, thread count = fastest of a probe)",
             "cpu_baseline": block,
             "e2e": {"value": v, "unit": "utt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -502,7 +511,8 @@ def main():
     e1.record()
     sync_all()
     ms_dev = max_over_ranks(e0.elapsed_time(e1) / args.steps)
-    launches = (launches_now() - n0) // args.steps
+    launches_total = launches_now() - n0  # kernels of this library launched inside the timed region (graph replays included)
+    launches = launches_total // args.steps
     clocks = sampler.stop() if sampler else None
 
     # one batch at a time (no lanes): the latency of a step and the reference point for the lanes' gain
@@ -578,20 +588,18 @@ def main():
             "metric": cfg["metric"], "value": value, "unit": "utt/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f16", "data": "synthetic",
-            "config": {"workload": cfg["workload"], "per_gpu_batch": BATCH, "global_batch": BATCH * world, "parallelism": f"dp{world}",
-                       "in_flight": LANES,
-                       "lanes": (f"{LANES} batches of {BATCH} in flight per GPU, each on its own stream with its own search state "
-                                 "(parallel.LanePool); a step is one batch through the whole path, ms_per_step = time of the K steps / K"
-                                 if LANES > 1 else "one batch at a time"),
-                       "l2": "working set (3.5 GB fp16 weights + activations) >> 126 MB L2, no explicit flush",
-                       "weights": "random-init, seeded", "accumulate": "f32",
-                       "decoder_step": "persistent kernel" if eng.decode_fused else "launch chain in a CUDA graph"},
+            "config": workload_config(cfg, BATCH, world),
+            "pipeline": {"in_flight": LANES,
+                         "lanes": (f"{LANES} batches of {BATCH} in flight per GPU, each on its own stream with its own search state "
+                                   "(parallel.LanePool); a step is one batch through the whole path, ms_per_step = time of the K steps / K"
+                                   if LANES > 1 else "one batch at a time"),
+                         "decoder_step": "persistent kernel" if eng.decode_fused else "launch chain in a CUDA graph"},
             "rtf": ms_dev * 1e-3 / (10.0 * BATCH),
             "serial": {"ms_per_step": ms_serial, "value": world * BATCH / (ms_serial * 1e-3), "unit": "utt/s",
                        "what": "the same step with one batch in flight (latency of a batch; SB_LANES=1 makes this the headline)"},
             "e2e": {"value": e2e_value, "unit": "utt/s", "h2d_bytes_per_step": xch.h2d_bytes, "d2h_bytes_per_step": xch.d2h_bytes,
                     "ms_per_step": ms_e2e, "overlap": "inputs of later steps and outputs of earlier steps move on side streams (exchange on the main thread, compute on the lanes)"},
-            "gpu_launches": int(launches),
+            "gpu_launches": int(launches_total), "gpu_launches_per_step": int(launches),
             "clocks": clocks,
         }
         if world == 1:
