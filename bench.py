@@ -648,7 +648,9 @@ def main():
                 line["parity"] = parity_block(tr, ref, waves_dev, task)
             except Exception as ex:  # the bench line must survive a parity failure and show it
                 line["parity"] = {"error": repr(ex)}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
+    if pool is not None:
+        pool.close()
     if world > 1:
         dist.destroy_process_group()
 
