@@ -371,6 +371,17 @@ def parity_block(tr, ref, waves_dev, task):
         u = speech.units[0]
         out["units_len"] = [len(u), len(u_ref)]
         out["units_differing"] = int(sum(a != b for a, b in zip(u, u_ref)) + abs(len(u) - len(u_ref)))
+        if out["units_differing"] and len(u) == len(u_ref) and "logits" in ref:
+            # margin audit of the differing units: the oracle's own top-1 / top-2 unit logits at those positions - an fp16
+            # argmax can only flip where the fp32 margin is inside the logit noise (4e-2 abs at full width)
+            try:
+                pos = [i for i, (a, b) in enumerate(zip(u, u_ref)) if a != b]
+                top2 = ref["logits"][0].float()[pos].topk(2, dim=-1).values
+                margins = top2[:, 0] - top2[:, 1]
+                out["units_oracle_top2_margin_at_diffs"] = [round(float(m), 4) for m in margins]
+                out["units_near_tie"] = bool(float(margins.max()) < 5e-2)
+            except Exception as ex:  # the audit must never cost the bench line
+                out["units_audit_error"] = repr(ex)
         w, w_ref = speech.audio_wavs[0].float().cpu().flatten(), ref["wavs"][0].flatten()
         n = min(w.numel(), w_ref.numel())
         out["wav_max_abs_err"] = float((w[:n] - w_ref[:n]).abs().max()) if out["units_differing"] == 0 else None
