@@ -24,6 +24,8 @@ extern "C" ggml_tensor* ConvModule_forward(fairseq2_model& model, const std::str
 extern "C" ggml_tensor* StandardConformerEncoderLayer_forward(fairseq2_model& model, const std::string& prefix, ggml_tensor* seqs,
                                                               ggml_tensor* padding_mask);
 
+extern "C" ggml_tensor* WaveformToFbank_forward(fairseq2_model& model, const std::string& prefix, ggml_tensor* waveform);
+
 namespace {
 
 std::int64_t double_bits(double v) {
@@ -203,6 +205,31 @@ int fs2ref_conformer(int n_tensors, const char** names, const float** data, cons
   ggml_free(ctx);
   ggml_free(wctx);
   return 0;
+}
+
+// WaveformToFbank_forward (fairseq2.cpp:553-602): knf log-mel frames of an already scaled (x 2**15) waveform, per-bin
+// standardisation over time (ggml_norm: biased variance, eps 1e-5), an odd last frame dropped, two frames stacked per
+// row (the Wav2Vec2FbankFeatureExtractor stride).  out [rows][cols] with cols = 160; returns 0, or -1 if `capacity`
+// floats do not hold the result.
+int fs2ref_waveform_to_fbank(const float* wave_scaled, int n_samples, float* out, int capacity, int* rows, int* cols) {
+  fairseq2_model model;
+  ggml_context* ctx = make_ctx(256u << 20);
+  model.ctx = ctx;
+  ggml_tensor* w = ggml_new_tensor_2d(ctx, GGML_TYPE_F32, n_samples, 1);
+  std::memcpy(w->data, wave_scaled, ggml_nbytes(w));
+  ggml_tensor* y = WaveformToFbank_forward(model, "", w);
+  ggml_cgraph* gf = ggml_new_graph(ctx);
+  ggml_build_forward_expand(gf, y);
+  ggml_graph_compute_with_ctx(ctx, gf, 1);
+  *cols = (int)y->ne[0];
+  *rows = (int)y->ne[1];
+  int rc = -1;
+  if ((long long)(*rows) * (*cols) <= capacity) {
+    std::memcpy(out, y->data, ggml_nbytes(y));
+    rc = 0;
+  }
+  ggml_free(ctx);
+  return rc;
 }
 
 }  // extern "C"
